@@ -1,0 +1,148 @@
+/*
+ * hmmer_oracle.h -- CPU restatement of HMMER3 `hmmsearch` (the arithmetic CheckM reaches through
+ * os.system at checkm/hmmer.py:70-71 with the flags at checkm/markerGeneFinder.py:141).
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under checkm_b200/ may include, link or call this; only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do.
+ *
+ * PARITY UNPINNED for the search arithmetic: HMMER's sources are not under /root/reference and no
+ * hmmsearch binary exists in the build container.  The algorithm is restated from
+ * the published HMMER 3.1b2 design (Eddy 2011, "Accelerated profile HMM searches"; Eddy 2008) --
+ * see SURVEY.md Appendix A.  What IS pinned: the HMM file parser against the reference's own fixture
+ * custom_marker_sets/cpr_43_markers.hmm, and the score statistics against that file's STATS lines
+ * (calibrated by the real HMMER 3.1b2) -- tests/test_oracle_stats.py.
+ */
+#ifndef HMMER_ORACLE_H
+#define HMMER_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_K   20
+#define ORC_KP  29
+
+enum { ORC_MM = 0, ORC_MI, ORC_MD, ORC_IM, ORC_II, ORC_DM, ORC_DD, ORC_NT };
+enum { ORC_MMU = 0, ORC_MLAMBDA, ORC_VMU, ORC_VLAMBDA, ORC_FTAU, ORC_FLAMBDA };
+
+typedef struct {
+  char   name[128];
+  char   acc[64];
+  char   desc[256];
+  int    M;
+  float *mat;      /* (M+1)*20 match emission probabilities, node 0 unused          */
+  float *ins;      /* (M+1)*20 insert emission probabilities                       */
+  float *t;        /* (M+1)*7  transition probabilities, file order MM MI MD IM II DM DD */
+  float  compo[ORC_K];
+  int    has_compo;
+  float  ga[2], tc[2], nc[2];
+  int    has_ga, has_tc, has_nc;
+  float  evparam[6];
+  int    has_stats;
+} orc_hmm;
+
+typedef struct {
+  int      M;
+  const orc_hmm *hmm;
+  /* generic log-odds profile (local, length-independent part) */
+  float   *tsc;        /* (M+1)*7 log transitions; rows 0 and M are -inf              */
+  float   *bm;         /* (M+1)   log local entry B->M_k                              */
+  float   *msc;        /* ORC_KP*(M+1) match log-odds, [x*(M+1)+k]                    */
+  /* MSV filter (8-bit costs) */
+  uint8_t *rbv;        /* ORC_KP*(M+1)                                                */
+  uint8_t  tbm_b, tec_b, base_b, bias_b;
+  float    scale_b;
+  /* Viterbi filter (16-bit scores) */
+  int16_t *rwv;        /* ORC_KP*(M+1)                                                */
+  int16_t *twv;        /* (M+1)*8: [k*8 + {BM,MM,IM,DM,MD,MI,II,DD}]                  */
+  int16_t  base_w, xw_e_loop, xw_e_move, ddbound_w;
+  float    scale_w;
+  /* Forward/Backward (odds ratios) */
+  float   *rfv;        /* ORC_KP*(M+1)                                                */
+  float   *tfv;        /* (M+1)*8 same order as twv                                   */
+} orc_profile;
+
+/* one reported (or unreported) domain of a hit */
+typedef struct {
+  int    ienv, jenv;
+  int    hmmfrom, hmmto, sqfrom, sqto;
+  float  envsc;          /* nats */
+  float  domcorrection;  /* nats */
+  float  dombias;        /* nats */
+  float  oasc;
+  float  bitscore;       /* bits */
+  double lnP;
+  int    is_reported;
+} orc_domain;
+
+typedef struct {
+  int    seqidx;
+  int    model;
+  int    L;
+  float  pre_score, score, sum_score;   /* bits */
+  double lnP;
+  int    ndom, nreported, nregions, nclustered, nenvelopes;
+  int    is_reported;
+  orc_domain *dcl;
+} orc_hit;
+
+/* filter outcomes for one (profile, sequence) pair; used by parity tests */
+typedef struct {
+  int    msv_xJ;          /* final xJ byte, or 256 on overflow                        */
+  float  msv_sc;          /* nats (INFINITY on overflow)                              */
+  float  nullsc, filtersc;
+  float  vit_sc, fwd_sc;  /* nats; NAN when the stage was not reached                 */
+  int    passed_msv, passed_bias, passed_vit, passed_fwd;
+} orc_filter_result;
+
+/* ---- alphabet ---- */
+int  orc_digitize(const char *seq, int n, uint8_t *dsq);   /* returns #invalid symbols */
+
+/* ---- HMM file ---- */
+int  orc_hmmfile_read(const char *path, orc_hmm **ret_hmms, int *ret_n);
+void orc_hmms_free(orc_hmm *hmms, int n);
+orc_hmm *orc_hmm_at(orc_hmm *hmms, int i);
+
+/* ---- profile ---- */
+orc_profile *orc_profile_create(const orc_hmm *hmm);
+void         orc_profile_free(orc_profile *p);
+
+/* ---- individual stages (dsq is 0-based, length L) ---- */
+float orc_null1(int L);
+int   orc_msv(const orc_profile *p, const uint8_t *dsq, int L, float *ret_sc, int *ret_xJ);
+int   orc_ssv_xe(const orc_profile *p, const uint8_t *dsq, int L);   /* max xE with J disabled */
+float orc_biasfilter(const orc_profile *p, const uint8_t *dsq, int L);
+int   orc_vitfilter(const orc_profile *p, const uint8_t *dsq, int L, float *ret_sc);
+int   orc_forward_parser(const orc_profile *p, const uint8_t *dsq, int L, float *ret_sc);
+int   orc_backward_parser(const orc_profile *p, const uint8_t *dsq, int L, float *ret_sc);
+int   orc_filters(const orc_profile *p, const uint8_t *dsq, int L, orc_filter_result *r);
+
+/* ---- full per-target pipeline; returns 1 and fills *hit if the target reaches the hit list ---- */
+int   orc_pipeline(const orc_profile *p, const uint8_t *dsq, int L, orc_hit *hit);
+
+/* ---- search: all models x all sequences, thresholds E<=Ecut, domE<=domEcut, Z=nseq ---- */
+typedef struct {
+  int      nhits;
+  orc_hit *hits;       /* sorted per model by lnP, thresholded flags set                */
+  double   Z;
+  double  *domZ;       /* per model                                                    */
+  int      nmodels;
+} orc_results;
+
+orc_results *orc_search(orc_profile **profs, int nmodels,
+                        const uint8_t *residues, const int64_t *offsets, int nseq,
+                        double Ecut, double domEcut, int nthreads);
+void orc_results_free(orc_results *r);
+int  orc_results_nhits(const orc_results *r);
+const orc_hit *orc_results_hit(const orc_results *r, int i);
+const orc_domain *orc_hit_domain(const orc_hit *h, int d);
+
+/* domtblout text for one search (names/descriptions supplied by the caller) */
+int orc_write_domtblout(const orc_results *r, orc_profile **profs,
+                        const char **seqnames, const char **seqdescs, const char *path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
