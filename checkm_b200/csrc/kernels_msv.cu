@@ -1,0 +1,287 @@
+// kernels_msv.cu -- stage 1 of the cascade: the ungapped (SSV) pre-filter over every (ORF x HMM) pair, and the
+// exact MSV filter for the few pairs it forwards.  Replaces the MSV stage of the hmmsearch process CheckM spawns
+// (checkm/hmmer.py:70-71); >97% of all DP cells of a search are scored here.
+//
+// Arithmetic (bit-exact with the 8-bit MSV definition).  The MSV cell update is
+//     sv(i,k) = sat0( min255( max(sv(i-1,k-1), xB) + bias ) - cost_k(x_i) )
+// With the J state idle, xB is the constant xB0 = base - tjb(L) - tbm(M), and w = max(sv, xB0) obeys
+//     w(i,k) = max( w(i-1,k-1) + (bias - cost), xB0 ).
+// We carry u = w - xB0 >= 0 in int16 lanes: u' = max(u + d, 0) with d = bias - cost -- ONE DPX instruction
+// (VIADDMNMX.S16x2) for two cells, and the running row maximum is folded two words at a time (VIMNMX3.S16x2).
+// The J state can only matter once some xE exceeds base + tec, so any pair whose u_max reaches either that bound
+// or (conservatively) the filter's pass threshold is re-scored by the exact byte-for-byte MSV kernel below; all
+// other pairs are provably rejected by the real filter.  No value ever has to be exact once it is past the bound,
+// so int16 wrap-around after thousands of rows is harmless (the maximum was recorded before the wrap).
+#include "engine.hpp"
+#include "device_utils.cuh"
+#include "stages.hpp"
+
+namespace ckm {
+
+// ------------------------------------------------------------------------------------------------
+// SSV pre-filter
+// ------------------------------------------------------------------------------------------------
+
+template <int J> __host__ __device__ constexpr int tile_table_bytes() { return KPAD * 128 * J; }
+template <int J> __host__ __device__ constexpr int tile_block_bytes() { return KPAD * 128 * J + 768; }
+
+
+template <int J>
+__device__ __forceinline__ void ssv_rows(const uint8_t *__restrict__ res, int L, uint32_t tile_smem, int lane, uint32_t sel,
+                                         const int16_t *bnd_in, int16_t *bnd_out, uint32_t (&u)[J], uint32_t &xE) {
+  constexpr int G = J / 4;
+  const uint4 *rp = reinterpret_cast<const uint4 *>(res);
+  const int nblk = (L + 15) >> 4;
+  uint4 cur = __ldg(rp);
+  const uint32_t lane_off = tile_smem + lane * 16;
+  for (int b = 0; b < nblk; ++b) {
+    uint4 nxt = (b + 1 < nblk) ? __ldg(rp + b + 1) : cur;
+    const uint32_t w4[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const uint32_t x = (w4[r >> 2] >> (8 * (r & 3))) & 0xffu;
+      const uint32_t row = lane_off + x * (128 * J);
+      uint4 e[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) e[g] = lds128(row + g * 512);
+      uint32_t bndw = 0;
+      if (bnd_in != nullptr) {              // chained tile: cell 0 continues the previous chunk's last cell
+        const int i = b * 16 + r;
+        bndw = (i > 0) ? (uint32_t)(uint16_t)bnd_in[i - 1] : 0u;
+      }
+      const uint32_t sh = __shfl_sync(0xffffffffu, u[J - 1], (lane + 31) & 31);
+#pragma unroll
+      for (int q = J - 1; q >= 1; --q) {
+        const uint32_t d = (&e[q >> 2].x)[q & 3];
+        u[q] = __viaddmax_s16x2(u[q - 1], d, 0u);
+      }
+      const uint32_t p0 = __byte_perm(sh, bndw, sel);
+      u[0] = __viaddmax_s16x2(p0, e[0].x, 0u);
+#pragma unroll
+      for (int q = 0; q < J; q += 2) xE = __vimax3_s16x2(xE, u[q], u[q + 1]);
+      if (bnd_out != nullptr && lane == 31) bnd_out[b * 16 + r] = (int16_t)(u[J - 1] >> 16);
+    }
+    cur = nxt;
+  }
+}
+
+template <int J>
+__global__ void __launch_bounds__(SSV_WARPS * 32, 1) ssv_kernel(SsvParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int s_unit, s_item;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t sel = (lane == 0) ? 0x1054u : 0x3210u;
+  constexpr int TB = tile_block_bytes<J>();
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  __syncthreads();
+  uint32_t phase = 0;
+  int cur_group = -1;
+  unsigned long long my_cells = 0;
+  int16_t *bndA = p.bnd ? p.bnd + ((int64_t)(blockIdx.x * SSV_WARPS + warp) * 2) * p.bnd_stride : nullptr;
+  int16_t *bndB = p.bnd ? bndA + p.bnd_stride : nullptr;
+
+  while (true) {
+    __syncthreads();                       // everybody is done with the previous unit (tables + s_item)
+    if (tid == 0) { s_unit = atomicAdd(p.unit_counter, 1); s_item = 0; }
+    __syncthreads();
+    const int unit = s_unit;
+    if (unit >= p.ngroups * p.nchunks) break;
+    const int gi = unit / p.nchunks, chunk = unit % p.nchunks;
+    const TileGroup grp = p.groups[p.group_list[gi]];
+    if (gi != cur_group) {                 // stage this group's tables (TMA bulk copies, one per tile)
+      cur_group = gi;
+      if (tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&bar, (uint32_t)grp.table_bytes);
+        for (int t = 0; t < grp.ntiles; ++t)
+          bulk_g2s(smem_base + t * TB, p.tile_blob + grp.table_off + (int64_t)t * TB, TB, &bar);
+      }
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+    }
+    const int s_begin = chunk * p.seq_chunk;
+    const int s_count = min(p.seq_chunk, p.nseq - s_begin);
+    const int nitems = s_count * grp.nchains;
+    while (true) {
+      int it = 0;
+      if (lane == 0) it = atomicAdd(&s_item, 1);
+      it = __shfl_sync(0xffffffffu, it, 0);
+      if (it >= nitems) break;
+      const int s = p.order[s_begin + it / grp.nchains];
+      const int chain = grp.first_chain + it % grp.nchains;
+      const int L = p.len[s];
+      if (L == 0) continue;
+      const int t0 = p.chain_first_tile[chain], nt = p.chain_ntiles[chain];
+      const int sbin = p.bin[s];
+      if (p.tile_active != nullptr && !p.tile_active[(int64_t)sbin * p.ntiles + t0]) continue;
+      const uint8_t *res = p.res + p.off[s];
+      const float Bs = p.msvB[s];
+      const int tjb = p.tjb[s];
+      bool chain_cand = false;
+      for (int tt = 0; tt < nt; ++tt) {
+        const int t = t0 + tt;
+        const int tl = t - grp.first_tile;                   // tile slot in shared memory
+        const uint32_t tsm = smem_base + tl * TB;
+        uint32_t u[J];
+#pragma unroll
+        for (int q = 0; q < J; ++q) u[q] = 0u;
+        uint32_t xE = 0u;
+        const int16_t *bin_ = (nt > 1 && tt > 0) ? ((tt & 1) ? bndA : bndB) : nullptr;
+        int16_t *bout = (nt > 1 && tt + 1 < nt) ? ((tt & 1) ? bndB : bndA) : nullptr;
+        ssv_rows<J>(res, L, tsm, lane, sel, bin_, bout, u, xE);
+        my_cells += (unsigned long long)L * (2 * J);
+        // ---- epilogue: does any slot reach the candidate bound? ----
+        const uint8_t *meta = smem + tl * TB + tile_table_bytes<J>();
+        const float *A = reinterpret_cast<const float *>(meta);
+        const int32_t *F = reinterpret_cast<const int32_t *>(meta + 256);
+        const int32_t *SM = reinterpret_cast<const int32_t *>(meta + 512);
+        const int ulo = (int)(int16_t)(xE & 0xffffu), uhi = (int)(int16_t)(xE >> 16);
+        const int thr_lo = min((int)floorf(A[lane] + Bs) - 1, F[lane] + tjb);
+        const int thr_hi = min((int)floorf(A[32 + lane] + Bs) - 1, F[32 + lane] + tjb);
+        const bool c_lo = (SM[lane] >= 0) && (ulo >= thr_lo);
+        const bool c_hi = (SM[32 + lane] >= 0) && (uhi >= thr_hi);
+        const unsigned m_lo = __ballot_sync(0xffffffffu, c_lo), m_hi = __ballot_sync(0xffffffffu, c_hi);
+        if ((m_lo | m_hi) == 0u) continue;
+        if (nt > 1) { chain_cand = true; continue; }
+        // which models of the tile own a firing slot?  lane j < nmodels answers for tile model j
+        const TileDesc td = p.tiles[t];
+        if (lane < td.nmodels) {
+          const TileModel tm = p.tile_models[td.first_model + lane];
+          const unsigned long long mask = ((unsigned long long)m_hi << 32) | m_lo;
+          const unsigned long long range = ((tm.nslots >= 64) ? ~0ull : ((1ull << tm.nslots) - 1ull)) << tm.slot0;
+          bool act = (mask & range) != 0ull;
+          if (act && p.model_active != nullptr) act = p.model_active[(int64_t)sbin * p.nmodels + tm.model] != 0;
+          if (act) {
+            const int pos = atomicAdd(p.cand_count, 1);
+            if (pos < p.cand_cap) p.cand[pos] = make_int2(s, tm.model);
+          }
+        }
+      }
+      if (nt > 1 && chain_cand && lane == 0) {
+        const TileModel tm = p.tile_models[p.tiles[t0].first_model];
+        bool act = true;
+        if (p.model_active != nullptr) act = p.model_active[(int64_t)sbin * p.nmodels + tm.model] != 0;
+        if (act) {
+          const int pos = atomicAdd(p.cand_count, 1);
+          if (pos < p.cand_cap) p.cand[pos] = make_int2(s, tm.model);
+        }
+      }
+    }
+  }
+  // statistics
+  my_cells = warp_sum_ull(my_cells);
+  if (lane == 0 && p.cells != nullptr) atomicAdd(p.cells, my_cells);
+}
+
+template __global__ void ssv_kernel<4>(SsvParams);
+template __global__ void ssv_kernel<8>(SsvParams);
+template __global__ void ssv_kernel<16>(SsvParams);
+
+int launch_ssv(int J, const SsvParams &p, int grid, size_t smem_bytes, cudaStream_t stream) {
+  cudaError_t e;
+  switch (J) {
+    case 4:
+      e = cudaFuncSetAttribute(ssv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ssv<4>)");
+      ssv_kernel<4><<<grid, SSV_WARPS * 32, smem_bytes, stream>>>(p);
+      break;
+    case 8:
+      e = cudaFuncSetAttribute(ssv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ssv<8>)");
+      ssv_kernel<8><<<grid, SSV_WARPS * 32, smem_bytes, stream>>>(p);
+      break;
+    case 16:
+      e = cudaFuncSetAttribute(ssv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ssv<16>)");
+      ssv_kernel<16><<<grid, SSV_WARPS * 32, smem_bytes, stream>>>(p);
+      break;
+    default: set_error("unsupported tile width"); return CKM_EINVAL;
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "ssv_kernel launch");
+  return CKM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact MSV filter: one warp per candidate pair, byte-for-byte the 8-bit recurrence with the J state.
+// Lane l owns model positions k = l+1, l+33, ...; the previous row lives in shared memory.
+// ------------------------------------------------------------------------------------------------
+
+
+__global__ void __launch_bounds__(MSV_WARPS * 32) msv_exact_kernel(MsvParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t *row0 = smem + (size_t)warp * 2 * p.row_bytes, *row1 = row0 + p.row_bytes;
+  const int ncand = min(*p.cand_count, p.cand_cap);
+  for (int c = blockIdx.x * MSV_WARPS + warp; c < ncand; c += gridDim.x * MSV_WARPS) {
+    const int2 pr = p.cand[c];
+    const int s = pr.x, m = pr.y;
+    const ModelScalars ms = p.ms[m];
+    const int M = ms.M, L = p.len[s];
+    const uint8_t *res = p.res + p.off[s];
+    const uint8_t *rbv = p.rbv + (int64_t)ms.off_cells * KPAD;
+    const int tjb = p.tjb[s];
+    const int tjbm = min(tjb + (int)ms.tbm_b, 255);
+    const int bias = ms.bias_b, base = ms.base_b, tec = ms.tec_b;
+    for (int k = lane; k <= M + 1; k += 32) { row0[k] = 0; row1[k] = 0; }
+    __syncwarp();
+    int xJ = 0, xB = max(base - tjbm, 0);
+    bool overflow = false;
+    uint8_t *prev = row0, *cur = row1;
+    for (int i = 0; i < L; ++i) {
+      const int x = res[i];
+      const uint8_t *rsc = rbv + (int64_t)x * ms.Mpad;
+      int xE = 0;
+      for (int k = lane + 1; k <= M; k += 32) {
+        int sv = max((int)prev[k - 1], xB);
+        sv = min(sv + bias, 255);
+        sv = max(sv - (int)rsc[k], 0);
+        cur[k] = (uint8_t)sv;
+        xE = max(xE, sv);
+      }
+      xE = warp_max_int(xE);
+      if (min(xE + bias, 255) == 255) { overflow = true; break; }
+      xE = max(xE - tec, 0);
+      xJ = max(xJ, xE);
+      xB = max(max(base, xJ) - tjbm, 0);
+      __syncwarp();
+      uint8_t *tmp = prev; prev = cur; cur = tmp;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      float usc;
+      if (overflow) usc = INFINITY;
+      else {
+        usc = ((float)(xJ - tjb) - (float)base);
+        usc = __fdiv_rn(usc, ms.scale_b);
+        usc = __fsub_rn(usc, 3.0f);
+      }
+      if (p.xj_dense != nullptr) p.xj_dense[(int64_t)p.model_slot[m] * p.nseq + s] = overflow ? 256 : xJ;
+      const float nullsc = p.nullsc[s];
+      const float seq_score = __fdiv_rn(__fsub_rn(usc, nullsc), 0.69314718055994529f);
+      const double P = gumbel_surv((double)seq_score, (double)ms.evparam[0], (double)ms.evparam[1]);
+      if (P <= p.F1) {
+        const int pos = atomicAdd(p.out_count, 1);
+        if (pos < p.out_cap) {
+          Candidate cd;
+          cd.seq = s; cd.model = m; cd.usc = usc; cd.filtersc = nullsc; cd.vitsc = 0.f; cd.fwdsc = 0.f; cd.P = P;
+          p.out[pos] = cd;
+        }
+      }
+    }
+  }
+}
+
+int launch_msv_exact(const MsvParams &p, int grid, cudaStream_t stream) {
+  const size_t smem = (size_t)MSV_WARPS * 2 * p.row_bytes;
+  cudaError_t e = cudaFuncSetAttribute(msv_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(msv_exact)");
+  msv_exact_kernel<<<grid, MSV_WARPS * 32, smem, stream>>>(p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "msv_exact_kernel launch");
+  return CKM_OK;
+}
+
+}  // namespace ckm

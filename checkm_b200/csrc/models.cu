@@ -1,0 +1,214 @@
+// models.cu -- model database on the device: per-model score tables for the survivor stages and the packed SSV tiles.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <stdexcept>
+#include "engine.hpp"
+
+namespace ckm {
+
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+const std::string &get_error() { return g_error; }
+int cuda_fail(cudaError_t e, const char *what) {
+  set_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what);
+  return CKM_ECUDA;
+}
+
+static const double kLog2 = 0.69314718055994529;
+
+template <class T>
+static int upload(T **dptr, const std::vector<T> &h) {
+  size_t bytes = std::max<size_t>(h.size() * sizeof(T), 16);
+  CKM_CUDA(cudaMalloc((void **)dptr, bytes));
+  if (!h.empty()) CKM_CUDA(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return CKM_OK;
+}
+
+static int tile_block_bytes_host(int J) { return KPAD * 128 * J + 768; }
+
+// Packs the models into SSV tiles (see engine.hpp) and builds the int16 emission-delta tables.
+static void build_tiles(ckm_models &db, std::vector<uint8_t> &blob) {
+  const int n = (int)db.models.size();
+  struct Item { int model, M; };
+  std::vector<Item> cls[3], longm;
+  for (int i = 0; i < n; ++i) {
+    int M = db.models[i].M;
+    if (M <= 255) cls[0].push_back({i, M});
+    else if (M <= 511) cls[1].push_back({i, M});
+    else if (M <= 1023) cls[2].push_back({i, M});
+    else longm.push_back({i, M});
+  }
+  const int Js[3] = {4, 8, 16};
+  struct HostTile { int J; std::vector<TileModel> tm; int used; int chain_prev, chain_next; };
+  std::vector<HostTile> tiles;
+  std::vector<std::pair<int, int>> chains;   // (first tile, ntiles)
+  std::vector<int> tile_class;
+  for (int c = 0; c < 3; ++c) {
+    auto &v = cls[c];
+    std::stable_sort(v.begin(), v.end(), [](const Item &a, const Item &b) { return a.M > b.M; });
+    const int J = Js[c];
+    size_t first = tiles.size();
+    for (const Item &it : v) {
+      int W = it.M / J + 1;
+      size_t t;
+      for (t = first; t < tiles.size(); ++t)
+        if (tiles[t].used + W <= 64 && (int)tiles[t].tm.size() < 32) break;
+      if (t == tiles.size()) { tiles.push_back({J, {}, 0, 0, 0}); tile_class.push_back(c); }
+      tiles[t].tm.push_back({it.model, tiles[t].used, W, 0});
+      tiles[t].used += W;
+    }
+    for (size_t t = first; t < tiles.size(); ++t) chains.push_back({(int)t, 1});
+  }
+  for (const Item &it : longm) {
+    int ncells = it.M + 1;                    // real cells + the mandatory padding cell
+    int nch = (ncells + 1023) / 1024;
+    chains.push_back({(int)tiles.size(), nch});
+    for (int c = 0; c < nch; ++c) {
+      HostTile ht{16, {}, 64, c > 0, c + 1 < nch};
+      ht.tm.push_back({it.model, 0, 64, c});
+      tiles.push_back(ht);
+      tile_class.push_back(3);
+    }
+  }
+  // groups: consecutive chains of equal J up to the shared-memory budget
+  const int64_t cap = 196608;
+  db.tiles.clear(); db.tile_models.clear(); db.groups.clear(); db.chain_first_tile.clear(); db.chain_ntiles.clear();
+  int64_t off = 0;
+  for (size_t t = 0; t < tiles.size(); ++t) {
+    TileDesc td{};
+    td.J = tiles[t].J; td.first_model = (int)db.tile_models.size(); td.nmodels = (int)tiles[t].tm.size();
+    td.chain_next = tiles[t].chain_next; td.chain_prev = tiles[t].chain_prev; td.table_off = off;
+    for (auto &tm : tiles[t].tm) db.tile_models.push_back(tm);
+    db.tiles.push_back(td);
+    off += tile_block_bytes_host(td.J);
+  }
+  blob.assign((size_t)off, 0);
+  {
+    TileGroup g{}; bool open = false; int64_t gbytes = 0;
+    for (size_t c = 0; c < chains.size(); ++c) {
+      int t0 = chains[c].first, nt = chains[c].second, J = tiles[t0].J;
+      int64_t need = (int64_t)nt * tile_block_bytes_host(J);
+      if (need > cap) throw std::runtime_error("model " + db.models[tiles[t0].tm[0].model].name + " is too long for the SSV tiles (M >= 3072)");
+      if (open && (g.J != J || gbytes + need > cap)) { g.table_bytes = gbytes; db.groups.push_back(g); open = false; }
+      if (!open) { g = TileGroup{}; g.J = J; g.first_tile = t0; g.ntiles = 0; g.nchains = 0; g.first_chain = (int)c; g.table_off = db.tiles[t0].table_off; gbytes = 0; open = true; }
+      g.ntiles += nt; g.nchains += 1; gbytes += need;
+      db.chain_first_tile.push_back(t0); db.chain_ntiles.push_back(nt);
+    }
+    if (open) { g.table_bytes = gbytes; db.groups.push_back(g); }
+  }
+  // tables
+  for (size_t t = 0; t < tiles.size(); ++t) {
+    const int J = tiles[t].J;
+    uint8_t *base = blob.data() + db.tiles[t].table_off;
+    int16_t *tab = reinterpret_cast<int16_t *>(base);
+    float *A = reinterpret_cast<float *>(base + KPAD * 128 * J);
+    int32_t *F = reinterpret_cast<int32_t *>(base + KPAD * 128 * J + 256);
+    int32_t *SM = reinterpret_cast<int32_t *>(base + KPAD * 128 * J + 512);
+    for (int s = 0; s < 64; ++s) { A[s] = 1e30f; F[s] = 1 << 28; SM[s] = -1; }
+    // default: padding everywhere
+    for (size_t i = 0; i < (size_t)KPAD * 64 * J; ++i) tab[i] = -32768;
+    for (size_t j = 0; j < tiles[t].tm.size(); ++j) {
+      const TileModel &tm = tiles[t].tm[j];
+      const Model &m = db.models[tm.model];
+      const int W1 = m.M + 1;
+      for (int sl = 0; sl < tm.nslots; ++sl) {
+        const int slot = tm.slot0 + sl;
+        A[slot] = db.models[tm.model].M > 0 ? 0.0f : 0.0f;   // filled below
+        SM[slot] = (int)j;
+        const int lane = slot & 31, half = slot >> 5;
+        for (int q = 0; q < J; ++q) {
+          const int k = tm.chunk * 1024 + sl * J + q + 1;      // model position of this cell
+          if (k > m.M) continue;
+          for (int x = 0; x < KP; ++x) {
+            const int d = (int)m.bias_b - (int)m.rbv[(size_t)x * W1 + k];
+            // word index inside residue row x: ((q/4)*32 + lane)*4 + (q%4); halves interleaved
+            const size_t w = (size_t)x * (J * 32) + ((size_t)(q >> 2) * 32 + lane) * 4 + (q & 3);
+            tab[w * 2 + half] = (int16_t)d;
+          }
+        }
+      }
+    }
+  }
+  // thresholds (per slot) need the per-model A, F
+  for (size_t t = 0; t < tiles.size(); ++t) {
+    const int J = tiles[t].J;
+    uint8_t *base = blob.data() + db.tiles[t].table_off;
+    float *A = reinterpret_cast<float *>(base + KPAD * 128 * J);
+    int32_t *F = reinterpret_cast<int32_t *>(base + KPAD * 128 * J + 256);
+    for (auto &tm : tiles[t].tm) {
+      const Model &m = db.models[tm.model];
+      const double F1 = 0.02;
+      const double sstar = (double)m.evparam[0] - std::log(-std::log(1.0 - F1)) / (double)m.evparam[1];
+      const float Am = (float)((double)m.tbm_b + (double)m.tec_b + (double)m.scale_b * kLog2 * sstar);
+      for (int sl = 0; sl < tm.nslots; ++sl) { A[tm.slot0 + sl] = Am; F[tm.slot0 + sl] = 4 + (int)m.tbm_b; }
+    }
+  }
+}
+
+int models_build_device(ckm_models &db) {
+  const int n = (int)db.models.size();
+  std::vector<ModelScalars> sc(n);
+  int64_t cols = 0;
+  db.maxM = 0;
+  for (int i = 0; i < n; ++i) {
+    const Model &m = db.models[i];
+    ModelScalars &s = sc[i];
+    std::memset(&s, 0, sizeof(s));
+    s.M = m.M; s.Mpad = ((m.M + 1) + 31) / 32 * 32; s.off_cells = (int32_t)cols;
+    cols += s.Mpad;
+    s.tbm_b = m.tbm_b; s.tec_b = m.tec_b; s.base_b = m.base_b; s.bias_b = m.bias_b;
+    s.base_w = m.base_w; s.xw_e_loop = m.xw_e_loop; s.xw_e_move = m.xw_e_move;
+    s.scale_b = m.scale_b; s.scale_w = m.scale_w;
+    for (int z = 0; z < 6; ++z) s.evparam[z] = m.evparam[z];
+    db.maxM = std::max(db.maxM, m.M);
+  }
+  if (cols > (int64_t)1 << 30) { set_error("model database too large"); return CKM_ENOMEM; }
+  db.total_cols = cols;
+  std::vector<uint8_t> rbv((size_t)cols * KPAD, 255);
+  std::vector<int16_t> rwv((size_t)cols * KPAD, -32768), twv((size_t)cols * T_N, -32768);
+  std::vector<float> rfv((size_t)cols * KPAD, 0.0f), tfv((size_t)cols * T_N, 0.0f), beo((size_t)n * KPAD * 2, 1.0f);
+  for (int i = 0; i < n; ++i) {
+    const Model &m = db.models[i];
+    const ModelScalars &s = sc[i];
+    const size_t W1 = (size_t)m.M + 1;
+    for (int x = 0; x < KP; ++x)
+      for (int k = 0; k <= m.M; ++k) {
+        const size_t d = ((size_t)s.off_cells * KPAD) + (size_t)x * s.Mpad + k;
+        rbv[d] = m.rbv[x * W1 + k]; rwv[d] = m.rwv[x * W1 + k]; rfv[d] = m.rfv[x * W1 + k];
+      }
+    for (int k = 0; k <= m.M; ++k)
+      for (int z = 0; z < T_N; ++z) {
+        twv[((size_t)s.off_cells + k) * T_N + z] = m.twv[(size_t)k * T_N + z];
+        tfv[((size_t)s.off_cells + k) * T_N + z] = m.tfv[(size_t)k * T_N + z];
+      }
+    for (int x = 0; x < KP; ++x) { beo[((size_t)i * KPAD + x) * 2] = m.bias_eo[x][0]; beo[((size_t)i * KPAD + x) * 2 + 1] = m.bias_eo[x][1]; }
+  }
+  int st;
+  if ((st = upload(&db.d_scalars, sc))) return st;
+  if ((st = upload(&db.d_rbv, rbv))) return st;
+  if ((st = upload(&db.d_rwv, rwv))) return st;
+  if ((st = upload(&db.d_twv, twv))) return st;
+  if ((st = upload(&db.d_rfv, rfv))) return st;
+  if ((st = upload(&db.d_tfv, tfv))) return st;
+  if ((st = upload(&db.d_bias_eo, beo))) return st;
+  std::vector<uint8_t> blob;
+  try { build_tiles(db, blob); } catch (const std::exception &ex) { set_error(ex.what()); return CKM_EINVAL; }
+  db.tile_blob_bytes = (int64_t)blob.size();
+  if ((st = upload(&db.d_tile_blob, blob))) return st;
+  if ((st = upload(&db.d_tiles, db.tiles))) return st;
+  if ((st = upload(&db.d_tile_models, db.tile_models))) return st;
+  if ((st = upload(&db.d_groups, db.groups))) return st;
+  if ((st = upload(&db.d_chain_first_tile, db.chain_first_tile))) return st;
+  if ((st = upload(&db.d_chain_ntiles, db.chain_ntiles))) return st;
+  return CKM_OK;
+}
+
+void models_free_device(ckm_models &db) {
+  cudaFree(db.d_scalars); cudaFree(db.d_rbv); cudaFree(db.d_rwv); cudaFree(db.d_twv); cudaFree(db.d_rfv); cudaFree(db.d_tfv);
+  cudaFree(db.d_bias_eo); cudaFree(db.d_tile_blob); cudaFree(db.d_tiles); cudaFree(db.d_tile_models); cudaFree(db.d_groups);
+  cudaFree(db.d_chain_first_tile); cudaFree(db.d_chain_ntiles);
+}
+
+}  // namespace ckm

@@ -1,0 +1,192 @@
+// search.cu -- the search driver: launches the filter cascade and the domain-definition stages on the engine's
+// stream and assembles the hit table.  Replaces the body of `hmmsearch` behind checkm/hmmer.py:61-74.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "engine.hpp"
+#include "stages.hpp"
+
+using namespace ckm;
+
+namespace ckm {
+
+// ---- device buffer with RAII ----
+struct DevBuf {
+  void *p = nullptr; size_t bytes = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t n) {
+    if (p) { cudaFree(p); p = nullptr; }
+    bytes = std::max<size_t>(n, 256);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaMalloc(workspace)"); }
+    return CKM_OK;
+  }
+  template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+enum { CTR_UNIT4 = 0, CTR_UNIT8, CTR_UNIT16, CTR_CAND, CTR_MSV, CTR_BIAS, CTR_VIT, CTR_FWD, CTR_ENV, CTR_DOM, CTR_N = 32 };
+
+struct ActiveMasks {
+  DevBuf tile_active, model_active, model_slot;
+  bool all_active = true;
+};
+
+// Builds the per-bin activity masks for a query subset.  bin_model_offsets == nullptr: the same nmodels queries for all bins.
+static int build_masks(const ckm_models *m, const ckm_seqdb *db, const int32_t *model_idx, int32_t nmodels,
+                       const int64_t *bin_model_offsets, ActiveMasks &am, std::vector<int32_t> &slot_of_model, cudaStream_t st) {
+  const int ndb = (int)m->models.size(), nbins = db->nbins, ntiles = (int)m->tiles.size();
+  slot_of_model.assign(ndb, -1);
+  bool all = (bin_model_offsets == nullptr) && (model_idx == nullptr || nmodels == ndb);
+  if (model_idx == nullptr) { for (int i = 0; i < ndb; ++i) slot_of_model[i] = i; }
+  else if (bin_model_offsets == nullptr) {
+    for (int i = 0; i < nmodels; ++i) {
+      if (model_idx[i] < 0 || model_idx[i] >= ndb) { set_error("model index out of range"); return CKM_EINVAL; }
+      if (slot_of_model[model_idx[i]] >= 0) { set_error("duplicate model index in query list"); return CKM_EINVAL; }
+      slot_of_model[model_idx[i]] = i;
+    }
+    if (all) for (int i = 0; i < ndb; ++i) if (slot_of_model[i] < 0) all = false;
+  }
+  am.all_active = all;
+  int rc;
+  if ((rc = am.model_slot.alloc(sizeof(int32_t) * ndb))) return rc;
+  CKM_CUDA(cudaMemcpyAsync(am.model_slot.p, slot_of_model.data(), sizeof(int32_t) * ndb, cudaMemcpyHostToDevice, st));
+  if (all) return CKM_OK;
+  std::vector<uint8_t> ma((size_t)nbins * ndb, 0), ta((size_t)nbins * ntiles, 0);
+  for (int b = 0; b < nbins; ++b) {
+    if (bin_model_offsets == nullptr) {
+      for (int i = 0; i < nmodels; ++i) ma[(size_t)b * ndb + model_idx[i]] = 1;
+    } else {
+      for (int64_t i = bin_model_offsets[b]; i < bin_model_offsets[b + 1]; ++i) {
+        if (model_idx[i] < 0 || model_idx[i] >= ndb) { set_error("model index out of range"); return CKM_EINVAL; }
+        ma[(size_t)b * ndb + model_idx[i]] = 1;
+      }
+    }
+    for (int t = 0; t < ntiles; ++t) {
+      const TileDesc &td = m->tiles[t];
+      uint8_t any = 0;
+      for (int j = 0; j < td.nmodels; ++j) any |= ma[(size_t)b * ndb + m->tile_models[td.first_model + j].model];
+      ta[(size_t)b * ntiles + t] = any;
+    }
+    // a chained model is addressed through its first tile
+  }
+  if ((rc = am.model_active.alloc(ma.size()))) return rc;
+  if ((rc = am.tile_active.alloc(ta.size()))) return rc;
+  CKM_CUDA(cudaMemcpyAsync(am.model_active.p, ma.data(), ma.size(), cudaMemcpyHostToDevice, st));
+  CKM_CUDA(cudaMemcpyAsync(am.tile_active.p, ta.data(), ta.size(), cudaMemcpyHostToDevice, st));
+  CKM_CUDA(cudaStreamSynchronize(st));     // host vectors go out of scope
+  return CKM_OK;
+}
+
+// Stage 1: SSV pre-filter over all pairs -> candidate list; exact MSV on the candidates -> pass list.
+struct Stage1 {
+  DevBuf cand, pass, bnd, glist, cells;
+  int32_t cand_cap = 0, pass_cap = 0;
+};
+
+static int run_stage1(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, ActiveMasks &am, int64_t n_pairs,
+                      Stage1 &s1, int32_t *xj_dense) {
+  cudaStream_t st = e->stream;
+  int rc;
+  s1.cand_cap = (int32_t)std::min<int64_t>(n_pairs, std::max<int64_t>(1 << 16, n_pairs / 6 + 65536));
+  s1.pass_cap = (int32_t)std::min<int64_t>(n_pairs, std::max<int64_t>(1 << 16, n_pairs / 12 + 65536));
+  if ((rc = s1.cand.alloc(sizeof(int2) * (size_t)s1.cand_cap))) return rc;
+  if ((rc = s1.pass.alloc(sizeof(Candidate) * (size_t)s1.pass_cap))) return rc;
+  if ((rc = s1.cells.alloc(sizeof(unsigned long long)))) return rc;
+  CKM_CUDA(cudaMemsetAsync(e->d_counters, 0, CTR_N * sizeof(int32_t), st));
+  CKM_CUDA(cudaMemsetAsync(s1.cells.p, 0, sizeof(unsigned long long), st));
+  const int nsm = e->prop.multiProcessorCount;
+  bool need_bnd = false;
+  for (int nt : m->chain_ntiles) need_bnd |= (nt > 1);
+  const int64_t bnd_stride = ((int64_t)db->maxL + 31) / 16 * 16;
+  if (need_bnd) { if ((rc = s1.bnd.alloc((size_t)nsm * SSV_WARPS_HOST * 2 * bnd_stride * sizeof(int16_t)))) return rc; }
+  // group lists per J
+  std::vector<int32_t> gl[3];
+  for (size_t g = 0; g < m->groups.size(); ++g) gl[m->groups[g].J == 4 ? 0 : (m->groups[g].J == 8 ? 1 : 2)].push_back((int32_t)g);
+  std::vector<int32_t> flat;
+  size_t goff[3];
+  for (int c = 0; c < 3; ++c) { goff[c] = flat.size(); flat.insert(flat.end(), gl[c].begin(), gl[c].end()); }
+  if ((rc = s1.glist.alloc(sizeof(int32_t) * std::max<size_t>(flat.size(), 1)))) return rc;
+  if (!flat.empty()) CKM_CUDA(cudaMemcpyAsync(s1.glist.p, flat.data(), sizeof(int32_t) * flat.size(), cudaMemcpyHostToDevice, st));
+  CKM_CUDA(cudaStreamSynchronize(st));
+
+  CKM_CUDA(cudaEventRecord(e->ev[0], st));
+  const int Js[3] = {4, 8, 16};
+  for (int c = 0; c < 3; ++c) {
+    if (gl[c].empty() || db->nseq == 0) continue;
+    SsvParams p{};
+    p.res = db->d_res; p.off = db->d_off; p.len = db->d_len; p.bin = db->d_bin;
+    p.msvB = db->d_msvB; p.tjb = db->d_tjb; p.order = db->d_order;
+    p.nseq = db->nseq;
+    p.seq_chunk = 128;
+    p.nchunks = (db->nseq + p.seq_chunk - 1) / p.seq_chunk;
+    p.groups = m->d_groups; p.group_list = s1.glist.as<int32_t>() + goff[c]; p.ngroups = (int32_t)gl[c].size();
+    p.tiles = m->d_tiles; p.tile_models = m->d_tile_models;
+    p.chain_first_tile = m->d_chain_first_tile; p.chain_ntiles = m->d_chain_ntiles;
+    p.tile_blob = m->d_tile_blob;
+    p.tile_active = am.all_active ? nullptr : am.tile_active.as<uint8_t>();
+    p.model_active = am.all_active ? nullptr : am.model_active.as<uint8_t>();
+    p.ntiles = (int32_t)m->tiles.size(); p.nmodels = (int32_t)m->models.size();
+    p.unit_counter = e->d_counters + CTR_UNIT4 + c;
+    p.cand = s1.cand.as<int2>(); p.cand_count = e->d_counters + CTR_CAND; p.cand_cap = s1.cand_cap;
+    p.bnd = need_bnd ? s1.bnd.as<int16_t>() : nullptr; p.bnd_stride = bnd_stride;
+    p.cells = s1.cells.as<unsigned long long>();
+    int64_t maxbytes = 0;
+    for (int g : gl[c]) maxbytes = std::max<int64_t>(maxbytes, m->groups[g].table_bytes);
+    const int64_t units = (int64_t)p.ngroups * p.nchunks;
+    const int grid = (int)std::min<int64_t>(nsm, units);
+    if ((rc = launch_ssv(Js[c], p, grid, (size_t)maxbytes, st))) return rc;
+    e->stats.kernel_launches++;
+  }
+  CKM_CUDA(cudaEventRecord(e->ev[1], st));
+  // exact MSV on the candidates
+  {
+    MsvParams p{};
+    p.res = db->d_res; p.off = db->d_off; p.len = db->d_len; p.nullsc = db->d_nullsc; p.tjb = db->d_tjb;
+    p.ms = m->d_scalars; p.rbv = m->d_rbv;
+    p.cand = s1.cand.as<int2>(); p.cand_count = e->d_counters + CTR_CAND; p.cand_cap = s1.cand_cap;
+    p.out = s1.pass.as<Candidate>(); p.out_count = e->d_counters + CTR_MSV; p.out_cap = s1.pass_cap;
+    p.xj_dense = xj_dense; p.model_slot = am.model_slot.as<int32_t>(); p.nseq = db->nseq;
+    p.row_bytes = (m->maxM + 2 + 15) / 16 * 16;
+    p.F1 = 0.02;
+    if ((rc = launch_msv_exact(p, nsm * 4, st))) return rc;
+    e->stats.kernel_launches++;
+  }
+  CKM_CUDA(cudaEventRecord(e->ev[2], st));
+  return CKM_OK;
+}
+
+}  // namespace ckm
+
+extern "C" {
+
+int ckm_msv_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_idx, int32_t nmodels,
+                   const ckm_seqdb *db, int32_t *xj_out) {
+  if (!e || !m || !db || !xj_out) { set_error("ckm_msv_scores: bad argument"); return CKM_EINVAL; }
+  cudaSetDevice(e->device);
+  if (model_idx == nullptr) nmodels = (int32_t)m->models.size();
+  ActiveMasks am; std::vector<int32_t> slot;
+  int rc = build_masks(m, db, model_idx, nmodels, nullptr, am, slot, e->stream);
+  if (rc) return rc;
+  const int64_t n = (int64_t)nmodels * db->nseq;
+  DevBuf dense;
+  if ((rc = dense.alloc(sizeof(int32_t) * (size_t)std::max<int64_t>(n, 1)))) return rc;
+  CKM_CUDA(cudaMemsetAsync(dense.p, 0xff, sizeof(int32_t) * (size_t)n, e->stream));
+  Stage1 s1;
+  std::memset(&e->stats, 0, sizeof(e->stats));
+  if ((rc = run_stage1(e, m, db, am, n, s1, dense.as<int32_t>()))) return rc;
+  int32_t ctr[CTR_N];
+  CKM_CUDA(cudaMemcpyAsync(ctr, e->d_counters, sizeof(ctr), cudaMemcpyDeviceToHost, e->stream));
+  unsigned long long cells = 0;
+  CKM_CUDA(cudaMemcpyAsync(&cells, s1.cells.p, sizeof(cells), cudaMemcpyDeviceToHost, e->stream));
+  CKM_CUDA(cudaMemcpyAsync(xj_out, dense.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+  CKM_CUDA(cudaStreamSynchronize(e->stream));
+  if (ctr[CTR_CAND] > s1.cand_cap || ctr[CTR_MSV] > s1.pass_cap) { set_error("candidate queue overflow"); return CKM_ECAPACITY; }
+  e->stats.n_pairs = n; e->stats.n_cells = (int64_t)cells;
+  e->stats.n_ssv_cand = ctr[CTR_CAND]; e->stats.n_past_msv = ctr[CTR_MSV];
+  cudaEventElapsedTime(&e->stats.ms_ssv, e->ev[0], e->ev[1]);
+  cudaEventElapsedTime(&e->stats.ms_msv, e->ev[1], e->ev[2]);
+  return CKM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,47 @@
+// stages.hpp -- parameter blocks and launchers of the device stages (kernels_*.cu), shared with search.cu.
+#pragma once
+#include "engine.hpp"
+
+namespace ckm {
+
+constexpr int SSV_WARPS = 16;
+constexpr int SSV_WARPS_HOST = SSV_WARPS;
+constexpr int MSV_WARPS = 8;
+
+// ---- stage 1a: SSV pre-filter over all (ORF x HMM) pairs ----
+struct SsvParams {
+  const uint8_t *res; const int64_t *off; const int32_t *len; const int32_t *bin;
+  const float *msvB; const int32_t *tjb; const int32_t *order;
+  int32_t nseq, seq_chunk, nchunks;
+  const TileGroup *groups; const int32_t *group_list; int32_t ngroups;
+  const TileDesc *tiles; const TileModel *tile_models;
+  const int32_t *chain_first_tile, *chain_ntiles;
+  const uint8_t *tile_blob;
+  const uint8_t *tile_active;      // [nbins][ntiles] or null
+  const uint8_t *model_active;     // [nbins][nmodels] or null
+  int32_t ntiles, nmodels;
+  int32_t *unit_counter;
+  int2 *cand; int32_t *cand_count; int32_t cand_cap;
+  int16_t *bnd; int64_t bnd_stride;   // per-warp boundary columns for chained tiles (2 buffers of bnd_stride each)
+  unsigned long long *cells;          // statistics: DP cells swept
+};
+
+int launch_ssv(int J, const SsvParams &p, int grid, size_t smem_bytes, cudaStream_t stream);
+
+// ---- stage 1b: exact MSV on the candidates ----
+struct MsvParams {
+  const uint8_t *res; const int64_t *off; const int32_t *len;
+  const float *nullsc; const int32_t *tjb;
+  const ModelScalars *ms; const uint8_t *rbv;
+  const int2 *cand; const int32_t *cand_count; int32_t cand_cap;
+  Candidate *out; int32_t *out_count; int32_t out_cap;
+  int32_t *xj_dense;           // optional [nmodel_slots][nseq] dense output for parity tests (null in production)
+  const int32_t *model_slot;   // database model index -> row of xj_dense
+  int32_t nseq;
+  int32_t row_bytes;           // shared-memory bytes of one DP row (>= maxM+2)
+  double F1;
+};
+
+int launch_msv_exact(const MsvParams &p, int grid, cudaStream_t stream);
+
+}  // namespace ckm

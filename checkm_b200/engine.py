@@ -1,0 +1,138 @@
+"""Thin Python object layer over the C ABI: Engine / Models / SeqDb.  All computation happens in libckm.so."""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+from ._lib import check, Hit, Stats, ModelInfo
+
+ALPHABET = "ACDEFGHIKLMNPQRSTVWY-BJZOUX*~"
+
+HIT_DTYPE = np.dtype([(n, {C.c_int32: np.int32, C.c_float: np.float32, C.c_double: np.float64}[t]) for n, t in Hit._fields_],
+                     align=True)
+assert HIT_DTYPE.itemsize == C.sizeof(Hit)
+
+
+def digitize(text):
+    """ASCII protein text -> uint8 codes (unknown symbols become X), via the library."""
+    b = text.encode() if isinstance(text, str) else bytes(text)
+    out = np.empty(len(b), dtype=np.uint8)
+    check(_lib.lib().ckm_digitize(b, len(b), out.ctypes.data))
+    return out
+
+
+class Models:
+    def __init__(self, engine, path):
+        self.engine = engine
+        self._h = C.c_void_p()
+        check(_lib.lib().ckm_models_load(engine._h, path.encode(), C.byref(self._h)))
+        self.path = path
+        self.n = _lib.lib().ckm_models_count(self._h)
+        self._info = None
+
+    def info(self):
+        if self._info is None:
+            out = []
+            for i in range(self.n):
+                mi = ModelInfo()
+                check(_lib.lib().ckm_models_info(self._h, i, C.byref(mi)))
+                out.append(mi)
+            self._info = out
+        return self._info
+
+    def find(self, key):
+        return _lib.lib().ckm_models_find(self._h, key.encode())
+
+    def select(self, keys):
+        arr = (C.c_char_p * len(keys))(*[k.encode() for k in keys])
+        idx = np.empty(max(self.n, 1), dtype=np.int32)
+        n = C.c_int()
+        check(_lib.lib().ckm_models_select(self._h, arr, len(keys), idx.ctypes.data, C.byref(n)))
+        return idx[:n.value].copy()
+
+    def write(self, idx, path):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        check(_lib.lib().ckm_models_write(self._h, idx.ctypes.data, len(idx), path.encode()))
+
+    def close(self):
+        if self._h:
+            _lib.lib().ckm_models_free(self._h)
+            self._h = C.c_void_p()
+
+
+class SeqDb:
+    def __init__(self, engine, residues, offsets, bin_of_seq=None, nbins=1):
+        self.engine = engine
+        self.residues = np.ascontiguousarray(residues, dtype=np.uint8)
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.nseq = len(self.offsets) - 1
+        self.nbins = int(nbins)
+        self.bin_of_seq = None if bin_of_seq is None else np.ascontiguousarray(bin_of_seq, dtype=np.int32)
+        self._h = C.c_void_p()
+        check(_lib.lib().ckm_seqdb_create(engine._h, self.residues.ctypes.data, self.offsets.ctypes.data, self.nseq,
+                                          None if self.bin_of_seq is None else self.bin_of_seq.ctypes.data,
+                                          self.nbins, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            _lib.lib().ckm_seqdb_free(self._h)
+            self._h = C.c_void_p()
+
+
+class Engine:
+    """One engine per process per GPU (a CUDA context cannot cross fork())."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        check(_lib.lib().ckm_init(int(device), C.byref(self._h)))
+        self.device = int(device)
+
+    def device_name(self):
+        buf = C.create_string_buffer(256)
+        check(_lib.lib().ckm_device_name(self._h, buf, 256))
+        return buf.value.decode()
+
+    def load_models(self, path):
+        return Models(self, path)
+
+    def seqdb(self, residues, offsets, bin_of_seq=None, nbins=1):
+        return SeqDb(self, residues, offsets, bin_of_seq, nbins)
+
+    def stats(self):
+        s = Stats()
+        check(_lib.lib().ckm_last_stats(self._h, C.byref(s)))
+        return s
+
+    def msv_scores(self, models, db, model_idx=None):
+        """Dense [nmodels, nseq] int32: exact MSV xJ byte for SSV candidates (256 = overflow), -1 otherwise."""
+        nm = models.n if model_idx is None else len(model_idx)
+        out = np.empty((nm, db.nseq), dtype=np.int32)
+        mi = None if model_idx is None else np.ascontiguousarray(model_idx, dtype=np.int32)
+        check(_lib.lib().ckm_msv_scores(self._h, models._h, None if mi is None else mi.ctypes.data, nm, db._h,
+                                        out.ctypes.data))
+        return out
+
+    def search(self, models, db, model_idx=None, E=0.1, domE=0.1, bin_model_offsets=None):
+        """Returns a numpy structured array of ckm_hit rows (domtblout rows)."""
+        hits = C.POINTER(Hit)()
+        n = C.c_int64()
+        mi = None if model_idx is None else np.ascontiguousarray(model_idx, dtype=np.int32)
+        if bin_model_offsets is None:
+            nm = models.n if mi is None else len(mi)
+            check(_lib.lib().ckm_search(self._h, models._h, None if mi is None else mi.ctypes.data, nm, db._h, E, domE,
+                                        C.byref(hits), C.byref(n)))
+        else:
+            bo = np.ascontiguousarray(bin_model_offsets, dtype=np.int64)
+            check(_lib.lib().ckm_search_per_bin(self._h, models._h, mi.ctypes.data, bo.ctypes.data, db._h, E, domE,
+                                                C.byref(hits), C.byref(n)))
+        if n.value == 0:
+            arr = np.zeros(0, dtype=HIT_DTYPE)
+        else:
+            buf = (C.c_char * (n.value * C.sizeof(Hit))).from_address(C.addressof(hits.contents))
+            arr = np.frombuffer(buf, dtype=HIT_DTYPE).copy()
+        _lib.lib().ckm_hits_free(hits)
+        return arr
+
+    def close(self):
+        if self._h:
+            _lib.lib().ckm_destroy(self._h)
+            self._h = C.c_void_p()

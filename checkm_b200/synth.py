@@ -198,3 +198,73 @@ def perturbed_model_lengths(rng, n, lo=30, hi=1500, mean=240):
     """Model lengths for the ~5k-HMM stand-in of configs #3-#5 (log-normal around the Pfam/TIGRFAM mean)."""
     x = rng.lognormal(mean=np.log(mean) - 0.18, sigma=0.6, size=n)
     return np.clip(x, lo, hi).astype(np.int64)
+
+
+def _nl(p):
+    return '      *' if p <= 0.0 else '%9.5f' % (-np.log(p))[:9].strip().rjust(9) if False else ('%.5f' % (-np.log(p)))
+
+
+def write_hmms(path, models, stats=None):
+    """Write PyHmm-like models as HMMER3/f text.  `stats[i]` = (msv_mu, vit_mu, fwd_tau, lambda) or None."""
+    with open(path, 'w') as f:
+        for i, h in enumerate(models):
+            M = h.M
+            mu = stats[i] if stats is not None else (-8.0 - 0.9 * np.log2(max(M, 2) / 50.0), -8.6 - 0.9 * np.log2(max(M, 2) / 50.0), -4.0, 0.71)
+            f.write('HMMER3/f [3.1b2 | February 2015]\n')
+            f.write('NAME  %s\n' % h.name)
+            if h.acc and h.acc != h.name:
+                f.write('ACC   %s\n' % h.acc)
+            f.write('LENG  %d\nALPH  amino\nRF    no\nMM    no\nCONS  no\nCS    no\nMAP   no\n' % M)
+            f.write('NSEQ  10\nEFFN  1.000000\nCKSUM 0\n')
+            ga = getattr(h, 'ga', None)
+            if ga is not None:
+                f.write('GA    %.2f %.2f;\n' % (ga, ga))
+            f.write('STATS LOCAL MSV      %8.4f  %.5f\n' % (mu[0], mu[3]))
+            f.write('STATS LOCAL VITERBI  %8.4f  %.5f\n' % (mu[1], mu[3]))
+            f.write('STATS LOCAL FORWARD  %8.4f  %.5f\n' % (mu[2], mu[3]))
+            f.write('HMM          ' + '        '.join(AMINO) + '   \n')
+            f.write('            m->m     m->i     m->d     i->m     i->i     d->m     d->d\n')
+            compo = h.mat[1:].mean(axis=0)
+            f.write('  COMPO   ' + '  '.join(_nl(p) for p in compo) + '\n')
+            for k in range(M + 1):
+                if k > 0:
+                    f.write('%7d   ' % k + '  '.join(_nl(p) for p in h.mat[k]) + '      %d - - - -\n' % k)
+                f.write('          ' + '  '.join(_nl(p) for p in h.ins[k]) + '\n')
+                f.write('          ' + '  '.join(('      *' if p <= 0 else _nl(p)) for p in h.t[k]) + '\n')
+            f.write('//\n')
+
+
+def resample_model(src_models, M, rng, name, acc=None):
+    """A model of length M stitched from random windows of real models (keeps realistic emission/transition rows)."""
+    mat = np.zeros((M + 1, 20))
+    ins = np.zeros((M + 1, 20))
+    t = np.zeros((M + 1, 7))
+    k = 1
+    first = src_models[int(rng.integers(len(src_models)))]
+    ins[0] = first.ins[0]
+    t[0] = first.t[0]
+    while k <= M:
+        s = src_models[int(rng.integers(len(src_models)))]
+        w = int(min(M - k + 1, rng.integers(10, 60), s.M - 2))
+        a = int(rng.integers(1, s.M - w))
+        mat[k:k + w] = s.mat[a:a + w]
+        ins[k:k + w] = s.ins[a:a + w]
+        t[k:k + w] = s.t[a:a + w]
+        k += w
+    # last node: no insert/delete exits (HMMER convention: MM=1? file stores m->m, *, m->d=*; i->m, i->i; d->m=1, d->d=*)
+    last = src_models[0]
+    t[M] = last.t[last.M]
+    ins[M] = last.ins[last.M]
+    h = PyHmm(name, acc if acc else name, M, mat, ins, t)
+    return h
+
+
+def make_model_db(path, src_path, lengths, seed=0, prefix='SYN'):
+    """Writes a synthetic HMM database with the given model lengths (configs #3-#5 stand-in)."""
+    rng = np.random.default_rng(seed)
+    src = read_hmms(src_path)
+    out = []
+    for i, M in enumerate(lengths):
+        out.append(resample_model(src, int(M), rng, '%s%05d' % (prefix, i), 'PF%05d.1' % (90000 + i) if i % 2 == 0 else 'TIGR%05d' % (90000 + i)))
+    write_hmms(path, out)
+    return out
