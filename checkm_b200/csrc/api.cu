@@ -178,7 +178,7 @@ int ckm_seqdb_create(ckm_engine *e, const uint8_t *residues, const int64_t *seq_
   db->len.resize(nseq);
   std::vector<int64_t> poff(nseq + 1, 0);
   const float scale_b = (float)(3.0 / 0.69314718055994529), scale_w = (float)(500.0 / 0.69314718055994529);
-  std::vector<float> nullsc(nseq), msvB(nseq);
+  std::vector<float> nullsc(nseq), msvB(nseq), lenA(nseq), lenB(nseq);
   std::vector<int32_t> tjb(nseq);
   std::vector<int16_t> tmove(nseq);
   int64_t pos = 0;
@@ -196,6 +196,7 @@ int ckm_seqdb_create(ckm_engine *e, const uint8_t *residues, const int64_t *seq_
     pos += (L + 15) / 16 * 16;
     // per-sequence length model: null1 score, MSV move cost, Viterbi move score
     float p1 = (float)L / (float)(L + 1);
+    lenA[s] = (float)L * logf(p1); lenB[s] = logf(1.0f - p1);
     nullsc[s] = (float)L * logf(p1) + logf(1.0f - p1);
     tjb[s] = unbiased_byteify_h(scale_b, logf(3.0f / (float)(L + 3)));
     tmove[s] = wordify_h(scale_w, logf(3.0f / (float)(L + 3)));
@@ -226,6 +227,8 @@ int ckm_seqdb_create(ckm_engine *e, const uint8_t *residues, const int64_t *seq_
   if (!st) st = up((void **)&db->d_nullsc, nullsc.data(), (size_t)nseq * sizeof(float));
   if (!st) st = up((void **)&db->d_tjb, tjb.data(), (size_t)nseq * sizeof(int32_t));
   if (!st) st = up((void **)&db->d_msvB, msvB.data(), (size_t)nseq * sizeof(float));
+  if (!st) st = up((void **)&db->d_lenA, lenA.data(), (size_t)nseq * sizeof(float));
+  if (!st) st = up((void **)&db->d_lenB, lenB.data(), (size_t)nseq * sizeof(float));
   if (!st) st = up((void **)&db->d_tmove_w, tmove.data(), (size_t)nseq * sizeof(int16_t));
   if (!st) st = up((void **)&db->d_order, order.data(), (size_t)nseq * sizeof(int32_t));
   if (!st) st = up((void **)&db->d_bin_nseq, db->bin_nseq.data(), (size_t)nbins * sizeof(int32_t));
@@ -239,7 +242,7 @@ void ckm_seqdb_free(ckm_seqdb *db) {
   if (!db) return;
   if (db->engine) cudaSetDevice(db->engine->device);
   cudaFree(db->d_res); cudaFree(db->d_off); cudaFree(db->d_len); cudaFree(db->d_bin); cudaFree(db->d_nullsc);
-  cudaFree(db->d_tjb); cudaFree(db->d_msvB); cudaFree(db->d_tmove_w); cudaFree(db->d_order); cudaFree(db->d_bin_nseq);
+  cudaFree(db->d_tjb); cudaFree(db->d_msvB); cudaFree(db->d_lenA); cudaFree(db->d_lenB); cudaFree(db->d_tmove_w); cudaFree(db->d_order); cudaFree(db->d_bin_nseq);
   delete db;
 }
 

@@ -59,6 +59,11 @@ __device__ __forceinline__ unsigned long long warp_sum_ull(unsigned long long v)
   return v;
 }
 
+__device__ __forceinline__ void atomicOr_u8(uint8_t *base, int64_t idx, unsigned bits) {
+  unsigned *w = reinterpret_cast<unsigned *>(base + (idx & ~(int64_t)3));
+  atomicOr(w, bits << (8 * (idx & 3)));
+}
+
 // ---- tail probabilities (double precision, as the reference pipeline computes them) ----
 __device__ __forceinline__ double gumbel_surv(double x, double mu, double lambda) {
   const double y = lambda * (x - mu);

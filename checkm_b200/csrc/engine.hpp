@@ -115,6 +115,7 @@ struct ckm_seqdb {
   float   *d_nullsc = nullptr;    // null1 score of each sequence
   int32_t *d_tjb = nullptr;       // MSV N/J/C move cost byte of each sequence
   float   *d_msvB = nullptr;      // sequence part of the SSV candidate threshold
+  float   *d_lenA = nullptr, *d_lenB = nullptr;   // L*log(p1), log(1-p1)
   int16_t *d_tmove_w = nullptr;   // Viterbi-filter N/J/C move score of each sequence
   int32_t *d_order = nullptr;     // sequence indices sorted by decreasing length (scheduling order)
   int32_t *d_bin_nseq = nullptr;

@@ -156,7 +156,7 @@ int models_build_device(ckm_models &db) {
     const Model &m = db.models[i];
     ModelScalars &s = sc[i];
     std::memset(&s, 0, sizeof(s));
-    s.M = m.M; s.Mpad = ((m.M + 1) + 31) / 32 * 32; s.off_cells = (int32_t)cols;
+    s.M = m.M; s.Mpad = ((m.M + 1) + 31) / 32 * 32 + 32; s.off_cells = (int32_t)cols;
     cols += s.Mpad;
     s.tbm_b = m.tbm_b; s.tec_b = m.tec_b; s.base_b = m.base_b; s.bias_b = m.bias_b;
     s.base_w = m.base_w; s.xw_e_loop = m.xw_e_loop; s.xw_e_move = m.xw_e_move;

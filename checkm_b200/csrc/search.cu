@@ -156,9 +156,98 @@ static int run_stage1(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
   return CKM_OK;
 }
 
+
+// Stages 2-4 on the MSV survivors: bias filter -> ViterbiFilter -> ForwardParser.  Lists ping-pong between two buffers.
+struct Stage2 {
+  DevBuf a, b;
+  int32_t cap = 0;
+  Candidate *fwd_list = nullptr;      // survivors of the Forward filter (points into a or b)
+};
+
+static int run_stage2(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, ActiveMasks &am, Stage1 &s1, Stage2 &s2,
+                      float *d_filtersc, float *d_vit, float *d_fwd, uint8_t *d_passed) {
+  cudaStream_t st = e->stream;
+  int rc;
+  s2.cap = s1.pass_cap;
+  if ((rc = s2.a.alloc(sizeof(Candidate) * (size_t)s2.cap))) return rc;
+  if ((rc = s2.b.alloc(sizeof(Candidate) * (size_t)s2.cap))) return rc;
+  const int nsm = e->prop.multiProcessorCount;
+  FilterParams p{};
+  p.res = db->d_res; p.off = db->d_off; p.len = db->d_len; p.lenA = db->d_lenA; p.lenB = db->d_lenB; p.tmove_w = db->d_tmove_w;
+  p.ms = m->d_scalars; p.bias_eo = m->d_bias_eo; p.rwv = m->d_rwv; p.twv = m->d_twv; p.rfv = m->d_rfv; p.tfv = m->d_tfv;
+  p.row_elems = ((m->maxM + 31) / 32) * 32 + 64;
+  p.F1 = 0.02; p.F2 = 1e-3; p.F3 = 1e-5;
+  p.dense_filtersc = d_filtersc; p.dense_vit = d_vit; p.dense_fwd = d_fwd; p.dense_passed = d_passed;
+  p.model_slot = am.model_slot.as<int32_t>(); p.nseq = db->nseq;
+  // bias: pass list (stage 1) -> a
+  p.in = s1.pass.as<Candidate>(); p.in_count = e->d_counters + CTR_MSV; p.in_cap = s1.pass_cap;
+  p.out = s2.a.as<Candidate>(); p.out_count = e->d_counters + CTR_BIAS; p.out_cap = s2.cap;
+  if ((rc = launch_bias(p, nsm * 8, st))) return rc;
+  CKM_CUDA(cudaEventRecord(e->ev[3], st));
+  // viterbi: a -> b
+  p.in = s2.a.as<Candidate>(); p.in_count = e->d_counters + CTR_BIAS; p.in_cap = s2.cap;
+  p.out = s2.b.as<Candidate>(); p.out_count = e->d_counters + CTR_VIT; p.out_cap = s2.cap;
+  if ((rc = launch_vit(p, nsm * 4, st))) return rc;
+  CKM_CUDA(cudaEventRecord(e->ev[4], st));
+  // forward: b -> a
+  p.in = s2.b.as<Candidate>(); p.in_count = e->d_counters + CTR_VIT; p.in_cap = s2.cap;
+  p.out = s2.a.as<Candidate>(); p.out_count = e->d_counters + CTR_FWD; p.out_cap = s2.cap;
+  if ((rc = launch_fwd(p, nsm * 4, st))) return rc;
+  CKM_CUDA(cudaEventRecord(e->ev[5], st));
+  e->stats.kernel_launches += 3;
+  s2.fwd_list = s2.a.as<Candidate>();
+  return CKM_OK;
+}
+
 }  // namespace ckm
 
 extern "C" {
+
+int ckm_filter_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_idx, int32_t nmodels,
+                      const ckm_seqdb *db, float *filtersc_out, float *vit_out, float *fwd_out, uint8_t *passed_out) {
+  if (!e || !m || !db || !filtersc_out || !vit_out || !fwd_out || !passed_out) { set_error("ckm_filter_scores: bad argument"); return CKM_EINVAL; }
+  cudaSetDevice(e->device);
+  if (model_idx == nullptr) nmodels = (int32_t)m->models.size();
+  ActiveMasks am; std::vector<int32_t> slot;
+  int rc = build_masks(m, db, model_idx, nmodels, nullptr, am, slot, e->stream);
+  if (rc) return rc;
+  const int64_t n = (int64_t)nmodels * db->nseq;
+  DevBuf dfs, dvit, dfwd, dpass;
+  const size_t nf = (size_t)std::max<int64_t>(n, 1);
+  if ((rc = dfs.alloc(sizeof(float) * nf)) || (rc = dvit.alloc(sizeof(float) * nf)) || (rc = dfwd.alloc(sizeof(float) * nf)) ||
+      (rc = dpass.alloc(nf + 4))) return rc;
+  // NaN-fill the float outputs, zero the flags
+  CKM_CUDA(cudaMemsetAsync(dfs.p, 0xff, sizeof(float) * nf, e->stream));
+  CKM_CUDA(cudaMemsetAsync(dvit.p, 0xff, sizeof(float) * nf, e->stream));
+  CKM_CUDA(cudaMemsetAsync(dfwd.p, 0xff, sizeof(float) * nf, e->stream));
+  CKM_CUDA(cudaMemsetAsync(dpass.p, 0, nf + 4, e->stream));
+  Stage1 s1; Stage2 s2;
+  std::memset(&e->stats, 0, sizeof(e->stats));
+  if ((rc = run_stage1(e, m, db, am, n, s1, nullptr))) return rc;
+  if ((rc = run_stage2(e, m, db, am, s1, s2, dfs.as<float>(), dvit.as<float>(), dfwd.as<float>(), dpass.as<uint8_t>()))) return rc;
+  int32_t ctr[CTR_N];
+  CKM_CUDA(cudaMemcpyAsync(ctr, e->d_counters, sizeof(ctr), cudaMemcpyDeviceToHost, e->stream));
+  CKM_CUDA(cudaMemcpyAsync(filtersc_out, dfs.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+  CKM_CUDA(cudaMemcpyAsync(vit_out, dvit.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+  CKM_CUDA(cudaMemcpyAsync(fwd_out, dfwd.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+  CKM_CUDA(cudaMemcpyAsync(passed_out, dpass.p, (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+  std::vector<Candidate> pass1((size_t)std::min<int64_t>(s1.pass_cap, std::max<int32_t>(1, s1.pass_cap)));
+  CKM_CUDA(cudaStreamSynchronize(e->stream));
+  if (ctr[CTR_CAND] > s1.cand_cap || ctr[CTR_MSV] > s1.pass_cap) { set_error("candidate queue overflow"); return CKM_ECAPACITY; }
+  // MSV pass flags come from the stage-1 pass list
+  pass1.resize((size_t)ctr[CTR_MSV]);
+  if (!pass1.empty()) CKM_CUDA(cudaMemcpy(pass1.data(), s1.pass.p, sizeof(Candidate) * pass1.size(), cudaMemcpyDeviceToHost));
+  for (const Candidate &c : pass1) passed_out[(int64_t)slot[c.model] * db->nseq + c.seq] |= 1;
+  e->stats.n_pairs = n;
+  e->stats.n_ssv_cand = ctr[CTR_CAND]; e->stats.n_past_msv = ctr[CTR_MSV]; e->stats.n_past_bias = ctr[CTR_BIAS];
+  e->stats.n_past_vit = ctr[CTR_VIT]; e->stats.n_past_fwd = ctr[CTR_FWD];
+  cudaEventElapsedTime(&e->stats.ms_ssv, e->ev[0], e->ev[1]);
+  cudaEventElapsedTime(&e->stats.ms_msv, e->ev[1], e->ev[2]);
+  cudaEventElapsedTime(&e->stats.ms_bias, e->ev[2], e->ev[3]);
+  cudaEventElapsedTime(&e->stats.ms_vit, e->ev[3], e->ev[4]);
+  cudaEventElapsedTime(&e->stats.ms_fwd, e->ev[4], e->ev[5]);
+  return CKM_OK;
+}
 
 int ckm_msv_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_idx, int32_t nmodels,
                    const ckm_seqdb *db, int32_t *xj_out) {

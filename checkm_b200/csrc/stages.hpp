@@ -44,4 +44,25 @@ struct MsvParams {
 
 int launch_msv_exact(const MsvParams &p, int grid, cudaStream_t stream);
 
+// ---- stages 2-4: bias filter, ViterbiFilter, ForwardParser on the survivors ----
+constexpr int VIT_WARPS = 4;
+constexpr int FWD_WARPS = 4;
+struct FilterParams {
+  const uint8_t *res; const int64_t *off; const int32_t *len;
+  const float *lenA, *lenB;          // L*log(p1), log(1-p1) of each sequence (host-computed, libm-exact)
+  const int16_t *tmove_w;
+  const ModelScalars *ms;
+  const float *bias_eo; const int16_t *rwv; const int16_t *twv; const float *rfv; const float *tfv;
+  const Candidate *in; const int32_t *in_count; int32_t in_cap;
+  Candidate *out; int32_t *out_count; int32_t out_cap;
+  int32_t row_elems;                 // shared-memory elements of one DP row
+  double F1, F2, F3;
+  // optional dense outputs for parity tests
+  float *dense_filtersc, *dense_vit, *dense_fwd; uint8_t *dense_passed;
+  const int32_t *model_slot; int32_t nseq;
+};
+int launch_bias(const FilterParams &p, int grid, cudaStream_t st);
+int launch_vit(const FilterParams &p, int grid, cudaStream_t st);
+int launch_fwd(const FilterParams &p, int grid, cudaStream_t st);
+
 }  // namespace ckm

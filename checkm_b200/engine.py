@@ -111,6 +111,19 @@ class Engine:
                                         out.ctypes.data))
         return out
 
+    def filter_scores(self, models, db, model_idx=None):
+        """Dense [nmodels, nseq] arrays: bias-filter null score, Viterbi and Forward filter scores (NaN where a stage
+        was not reached) and pass flags (bit0 MSV, bit1 bias, bit2 Viterbi, bit3 Forward)."""
+        nm = models.n if model_idx is None else len(model_idx)
+        fs = np.empty((nm, db.nseq), dtype=np.float32)
+        vs = np.empty((nm, db.nseq), dtype=np.float32)
+        fw = np.empty((nm, db.nseq), dtype=np.float32)
+        ps = np.empty((nm, db.nseq), dtype=np.uint8)
+        mi = None if model_idx is None else np.ascontiguousarray(model_idx, dtype=np.int32)
+        check(_lib.lib().ckm_filter_scores(self._h, models._h, None if mi is None else mi.ctypes.data, nm, db._h,
+                                           fs.ctypes.data, vs.ctypes.data, fw.ctypes.data, ps.ctypes.data))
+        return fs, vs, fw, ps
+
     def search(self, models, db, model_idx=None, E=0.1, domE=0.1, bin_model_offsets=None):
         """Returns a numpy structured array of ckm_hit rows (domtblout rows)."""
         hits = C.POINTER(Hit)()
