@@ -1,0 +1,359 @@
+// kernels_ensemble.cu -- multi-domain regions: Forward matrix of the region (multihit), 200 stochastic tracebacks with a
+// fixed-seed generator, per-trace null2 accumulation, single-linkage clustering of the sampled segments into envelopes
+// (SURVEY.md A.5 step 5).  One warp per region; the traceback state machine is warp-uniform, with the O(M) pieces
+// (E-state choice, null2 from state counts, link tests) spread over the lanes.
+#include <algorithm>
+#include <vector>
+#include "engine.hpp"
+#include "device_utils.cuh"
+#include "stages.hpp"
+#include "fwdback.cuh"
+
+namespace ckm {
+
+constexpr int NSAMPLES = 200;
+constexpr int SPCAP = 4096;           // sampled segments kept per region
+constexpr int MAXENV = 32;            // envelopes reported per region
+
+struct EnsembleParams {
+  DomdefParams d;
+  const Region *regions; const int32_t *multi_idx; int32_t nmulti;
+  const int64_t *scratch_off;         // per multi region, in floats
+  float *scratch;
+  Envelope *env_out; int32_t *env_count;      // [nmulti][MAXENV], [nmulti]
+};
+
+enum { ST_M = 1, ST_D, ST_I, ST_S, ST_N, ST_B, ST_E, ST_C, ST_T, ST_J };
+
+struct Lcg { uint32_t x; };
+__device__ __forceinline__ uint32_t mix3(uint32_t a, uint32_t b, uint32_t c) {
+  a -= b; a -= c; a ^= (c >> 13);
+  b -= c; b -= a; b ^= (a << 8);
+  c -= a; c -= b; c ^= (b >> 13);
+  a -= b; a -= c; a ^= (c >> 12);
+  b -= c; b -= a; b ^= (a << 16);
+  c -= a; c -= b; c ^= (b >> 5);
+  a -= b; a -= c; a ^= (c >> 3);
+  b -= c; b -= a; b ^= (a << 10);
+  c -= a; c -= b; c ^= (b >> 15);
+  return c;
+}
+__device__ __forceinline__ double lcg_random(Lcg &r) { r.x *= 69069u; r.x += 1u; return (double)r.x / 4294967296.0; }
+
+__device__ __forceinline__ int fchoose(Lcg &rng, float *pth, int N) {
+  float sum = 0.0f;
+  for (int i = 0; i < N; ++i) sum = __fadd_rn(sum, pth[i]);
+  if (sum != 0.0f) { const float s = (float)(1.0 / (double)sum); for (int i = 0; i < N; ++i) pth[i] = __fmul_rn(pth[i], s); }
+  else for (int i = 0; i < N; ++i) pth[i] = __fdiv_rn(1.0f, (float)N);
+  const float roll = (float)lcg_random(rng);
+  sum = 0.0f;
+  for (int i = 0; i < N; ++i) { sum = __fadd_rn(sum, pth[i]); if (roll < sum) return i; }
+  int i;
+  int guard = 0;
+  do { i = (int)(lcg_random(rng) * N); } while (pth[i] == 0.0f && ++guard < 64);
+  return i;
+}
+
+__device__ __forceinline__ bool sp_link(const int *a, const int *b) {   // {idx,i,j,k,m}
+  int nov = min(a[2], b[2]) - max(a[1], b[1]) + 1;
+  int n = min(a[2] - a[1] + 1, b[2] - b[1] + 1);
+  if ((float)nov / (float)n < 0.8f) return false;
+  nov = min(a[4], b[4]) - max(a[3], b[3]);
+  n = min(a[4] - a[3] + 1, b[4] - b[3] + 1);
+  if ((float)nov / (float)n < 0.8f) return false;
+  if (abs((a[1] - a[3]) - (b[1] - b[3])) > 4) return false;
+  if (abs((a[2] - a[4]) - (b[2] - b[4])) > 4) return false;
+  return true;
+}
+
+__global__ void __launch_bounds__(FWD_WARPS * 32) ensemble_kernel(EnsembleParams ep) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const DomdefParams &p = ep.d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *rowM = reinterpret_cast<float *>(smem) + (size_t)warp * 3 * p.row_elems;
+  float *rowI = rowM + p.row_elems, *rowD = rowI + p.row_elems;
+  for (int ri = blockIdx.x * FWD_WARPS + warp; ri < ep.nmulti; ri += gridDim.x * FWD_WARPS) {
+    const Region reg = ep.regions[ep.multi_idx[ri]];
+    const PairWork pw = p.pairs[reg.pair];
+    const ModelScalars ms = p.ms[pw.model];
+    FwdModel fm;
+    fm.M = ms.M; fm.Mpad = ms.Mpad;
+    fm.rfv = p.rfv + (int64_t)ms.off_cells * KPAD;
+    fm.tfv = reinterpret_cast<const float4 *>(p.tfv + (int64_t)ms.off_cells * T_N);
+    const int M = fm.M, Mpad = fm.Mpad, Lr = reg.j - reg.i + 1;
+    const int Q = max(2, (M + 3) / 4);
+    const uint8_t *res = p.res + p.off[pw.seq] + (reg.i - 1);
+    const Specials sp = make_specials(pw.L, true);
+    float *F = ep.scratch + ep.scratch_off[ri];
+    float *xf = F + (int64_t)(Lr + 1) * 3 * Mpad;
+    float *acc = xf + (int64_t)(Lr + 1) * X_NX, *val = acc + (Lr + 1);
+    int *spb = reinterpret_cast<int *>(val + (Lr + 1));       // SPCAP x 5
+    int *label = spb + SPCAP * 5;                            // SPCAP
+    int *epc = label + SPCAP;                                // max(Lr, M) + 2
+    int *segbuf = epc + max(Lr, M) + 2;                      // per-trace segments, right-to-left: 64 x 4
+    float *n2sc = p.n2sc + pw.row_off;
+    forward_rows<true>(fm, res, Lr, sp, rowM, rowI, rowD, lane, xf, F, 0, nullptr);
+    for (int pos = lane; pos <= Lr; pos += 32) acc[pos] = 0.0f;
+    __syncwarp();
+    Lcg rng; rng.x = mix3(42u, 87654321u, 12345678u); if (rng.x == 0) rng.x = 42;
+    int nsp = 0;
+    float *cm = rowM, *ci = rowI, *null2 = rowD;
+    for (int t = 0; t < NSAMPLES; ++t) {
+      for (int pos = lane; pos <= Lr; pos += 32) val[pos] = 1.0f;
+      __syncwarp();
+      int i = Lr, k = 0, s0 = ST_C, s1 = -1;
+      int nseg = 0;
+      int sqto = 0, hmmto = 0, sqfrom = 0, hmmfrom = 0, ldom = 0;
+      bool in_dom = false, failed = false;
+      long guard = 0;
+      const long gmax = 8L * (Lr + 2) * (M + 2);
+      while (s0 != ST_S) {
+        if (++guard > gmax) { failed = true; break; }
+        float pth[4];
+        if (s0 == ST_M) {
+          const float *dpp = F + (int64_t)(i - 1) * 3 * Mpad;
+          const float4 t0 = __ldg(fm.tfv + 2 * k);
+          pth[0] = __fmul_rn(xf[(int64_t)(i - 1) * X_NX + X_B], t0.x);
+          pth[1] = __fmul_rn(dpp[k - 1], t0.y);
+          pth[2] = __fmul_rn(dpp[2 * Mpad + k - 1], t0.z);
+          pth[3] = __fmul_rn(dpp[Mpad + k - 1], t0.w);
+          const int c = fchoose(rng, pth, 4);
+          s1 = (c == 0) ? ST_B : (c == 1) ? ST_M : (c == 2) ? ST_I : ST_D;
+          k--; i--;
+        } else if (s0 == ST_D) {
+          const float *dpc = F + (int64_t)i * 3 * Mpad;
+          const float4 t1 = __ldg(fm.tfv + 2 * (k - 1) + 1);
+          pth[0] = __fmul_rn(dpc[k - 1], t1.x);
+          pth[1] = __fmul_rn(dpc[Mpad + k - 1], t1.w);
+          s1 = fchoose(rng, pth, 2) == 0 ? ST_M : ST_D; k--;
+        } else if (s0 == ST_I) {
+          const float *dpp = F + (int64_t)(i - 1) * 3 * Mpad;
+          const float4 t1 = __ldg(fm.tfv + 2 * k + 1);
+          pth[0] = __fmul_rn(dpp[k], t1.y);
+          pth[1] = __fmul_rn(dpp[2 * Mpad + k], t1.z);
+          s1 = fchoose(rng, pth, 2) == 0 ? ST_M : ST_I; i--;
+        } else if (s0 == ST_N) {
+          s1 = (i == 0) ? ST_S : ST_N;
+        } else if (s0 == ST_C) {
+          pth[0] = (i > 0) ? __fmul_rn(xf[(int64_t)(i - 1) * X_NX + X_C], sp.nloop) : 0.0f;
+          pth[1] = __fmul_rn(xf[(int64_t)i * X_NX + X_E], sp.emove);
+          s1 = fchoose(rng, pth, 2) == 0 ? ST_C : ST_E;
+        } else if (s0 == ST_J) {
+          pth[0] = (i > 0) ? __fmul_rn(xf[(int64_t)(i - 1) * X_NX + X_J], sp.nloop) : 0.0f;
+          pth[1] = __fmul_rn(xf[(int64_t)i * X_NX + X_E], sp.eloop);
+          s1 = fchoose(rng, pth, 2) == 0 ? ST_J : ST_E;
+        } else if (s0 == ST_B) {
+          pth[0] = __fmul_rn(xf[(int64_t)i * X_NX + X_N], sp.nmove);
+          pth[1] = __fmul_rn(xf[(int64_t)i * X_NX + X_J], sp.nmove);
+          s1 = fchoose(rng, pth, 2) == 0 ? ST_N : ST_J;
+        } else if (s0 == ST_E) {
+          // choose among all M(i,k), D(i,k) in the striped enumeration order of the SIMD original:
+          // entry e = q*8 + r (match, k = r*Q+q+1) or q*8 + 4 + r (delete)
+          const float *dpc = F + (int64_t)i * 3 * Mpad;
+          const double roll = lcg_random(rng);
+          const float norm = (float)(1.0 / (double)xf[(int64_t)i * X_NX + X_E]);
+          const int nent = 8 * Q, per = (nent + 31) / 32;
+          const int e0 = lane * per, e1 = min(nent, e0 + per);
+          double part = 0.0;
+          for (int e = e0; e < e1; ++e) {
+            const int q = e >> 3, r = e & 3, isd = (e >> 2) & 1, kk = r * Q + q + 1;
+            const float v = (kk <= M) ? __fmul_rn(dpc[isd * Mpad + kk], norm) : 0.0f;
+            part += (double)v;
+          }
+          double incl = part;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const double up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+          const unsigned hitmask = __ballot_sync(0xffffffffu, roll < incl && e1 > e0);
+          int sel = -1;
+          if (hitmask != 0u) {
+            const int owner = __ffs(hitmask) - 1;
+            if (lane == owner) {
+              double sum = incl - part;
+              for (int e = e0; e < e1; ++e) {
+                const int q = e >> 3, r = e & 3, isd = (e >> 2) & 1, kk = r * Q + q + 1;
+                const float v = (kk <= M) ? __fmul_rn(dpc[isd * Mpad + kk], norm) : 0.0f;
+                sum += (double)v;
+                if (roll < sum) { sel = e; break; }
+              }
+              if (sel < 0) sel = e1 - 1;
+            }
+            sel = __shfl_sync(0xffffffffu, sel, owner);
+          }
+          if (sel < 0) { failed = true; break; }
+          { const int q = sel >> 3, r = sel & 3, isd = (sel >> 2) & 1; k = r * Q + q + 1; s1 = isd ? ST_D : ST_M; }
+          if (k > M) { failed = true; break; }
+          // a new domain starts (we walk right to left, so this is its end)
+          in_dom = true; sqto = 0; hmmto = 0; sqfrom = 0; hmmfrom = 0; ldom = 0;
+          for (int kk = lane; kk <= M; kk += 32) { cm[kk] = 0.0f; ci[kk] = 0.0f; }
+          __syncwarp();
+        } else { failed = true; break; }
+        // bookkeeping for the state just entered (coordinates k, i are those of s1)
+        if (in_dom) {
+          if (s1 == ST_M) {
+            if (sqto == 0) sqto = i;
+            if (hmmto == 0) hmmto = k;
+            sqfrom = i; hmmfrom = k; ldom++;
+            if (lane == 0) cm[k] += 1.0f;
+          } else if (s1 == ST_I) {
+            ldom++;
+            if (lane == 0) ci[k] += 1.0f;
+          } else if (s1 == ST_D) {
+            if (hmmto == 0) hmmto = k;
+            hmmfrom = k;
+          } else if (s1 == ST_B) {
+            // domain complete: null2 from its state usage, then the per-residue ratios of the aligned span
+            __syncwarp();
+            const float nrm = __fdiv_rn(1.0f, (float)ldom);
+            for (int kk = lane + 1; kk <= M; kk += 32) { cm[kk] *= nrm; ci[kk] *= nrm; }
+            __syncwarp();
+            for (int x = 0; x < K; ++x) {
+              const float *rp = fm.rfv + (int64_t)x * Mpad;
+              float part = 0.0f;
+              for (int kk = lane + 1; kk <= M; kk += 32) { part += cm[kk] * __ldg(rp + kk); part += ci[kk]; }
+              part = warp_sum_float(part);
+              if (lane == 0) null2[x] = part;
+            }
+            __syncwarp();
+            if (lane == 0) {
+              { float r = 0.f; r += null2[2]; r += null2[11]; null2[21] = __fdiv_rn(r, 2.0f); }
+              { float r = 0.f; r += null2[7]; r += null2[9];  null2[22] = __fdiv_rn(r, 2.0f); }
+              { float r = 0.f; r += null2[3]; r += null2[13]; null2[23] = __fdiv_rn(r, 2.0f); }
+              null2[24] = null2[8]; null2[25] = null2[1];
+              float rx = 0.f;
+              for (int x = 0; x < K; ++x) rx += null2[x];
+              null2[26] = __fdiv_rn(rx, 20.0f);
+              null2[20] = 1.0f; null2[27] = 1.0f; null2[28] = 1.0f; null2[29] = 1.0f;
+            }
+            __syncwarp();
+            // residues sqfrom+1 .. sqto get the ratio; sqfrom itself keeps 1.0 (as the reference does)
+            for (int pos = sqfrom + 1 + lane; pos <= sqto; pos += 32) val[pos] = null2[res[pos - 1]];
+            if (lane == 0 && nseg < 64) { segbuf[nseg * 4 + 0] = sqfrom; segbuf[nseg * 4 + 1] = sqto; segbuf[nseg * 4 + 2] = hmmfrom; segbuf[nseg * 4 + 3] = hmmto; }
+            nseg++;
+            in_dom = false;
+            __syncwarp();
+          }
+        }
+        if ((s1 == ST_N || s1 == ST_J || s1 == ST_C) && s1 == s0) i--;
+        s0 = s1;
+      }
+      __syncwarp();
+      if (failed) continue;
+      for (int pos = 1 + lane; pos <= Lr; pos += 32) acc[pos] += val[pos];
+      // append this trace's segments left to right
+      if (lane == 0) {
+        for (int z = min(nseg, 64) - 1; z >= 0; --z) {
+          if (nsp + 0 < SPCAP) {
+            int *e = spb + nsp * 5;
+            e[0] = t; e[1] = segbuf[z * 4 + 0] + reg.i - 1; e[2] = segbuf[z * 4 + 1] + reg.i - 1; e[3] = segbuf[z * 4 + 2]; e[4] = segbuf[z * 4 + 3];
+          }
+          nsp++;
+        }
+      }
+      nsp = __shfl_sync(0xffffffffu, nsp, 0);
+      __syncwarp();
+    }
+    nsp = min(nsp, SPCAP);
+    for (int pos = reg.i + lane; pos <= reg.j; pos += 32) n2sc[pos] = logf(__fdiv_rn(acc[pos - reg.i + 1], (float)NSAMPLES));
+    // ---- single-linkage clustering = connected components of the link graph (min-label propagation) ----
+    for (int h = lane; h < nsp; h += 32) label[h] = h;
+    __syncwarp();
+    for (int iter = 0; iter < 64; ++iter) {
+      int changed = 0;
+      const long npair = (long)nsp * (nsp - 1) / 2;
+      for (int a = 0; a < nsp; ++a) {
+        for (int b = a + 1 + lane; b < nsp; b += 32) {
+          const int la = label[a], lb = label[b];
+          if (la != lb && sp_link(spb + a * 5, spb + b * 5)) {
+            const int mn = min(la, lb);
+            atomicMin(&label[a], mn); atomicMin(&label[b], mn);
+            changed = 1;
+          }
+        }
+        __syncwarp();
+      }
+      (void)npair;
+      // pointer jumping
+      for (int h = lane; h < nsp; h += 32) { int l = label[h]; while (label[l] != l) l = label[l]; label[h] = l; }
+      __syncwarp();
+      if (!__any_sync(0xffffffffu, changed)) break;
+    }
+    // ---- significant clusters -> envelopes (lane 0; the lists are short) ----
+    if (lane == 0) {
+      int nout = 0;
+      Envelope *eo = ep.env_out + (int64_t)ri * MAXENV;
+      for (int c = 0; c < nsp; ++c) {
+        if (label[c] != c) continue;
+        int idx_of_last = -1, ninc = 0;
+        for (int h = 0; h < nsp; ++h) if (label[h] == c) { if (spb[h * 5] != idx_of_last) ninc++; idx_of_last = spb[h * 5]; }
+        if ((float)ninc / (float)NSAMPLES < 0.25f) continue;
+        int imin = 1 << 30, jmin = 1 << 30, imax = 0, jmax = 0;
+        for (int h = 0; h < nsp; ++h) if (label[h] == c) {
+          imin = min(imin, spb[h * 5 + 1]); imax = max(imax, spb[h * 5 + 1]);
+          jmin = min(jmin, spb[h * 5 + 2]); jmax = max(jmax, spb[h * 5 + 2]);
+        }
+        int cmv, best_i, best_j;
+        for (int z = 0; z <= imax - imin; ++z) epc[z] = 0;
+        for (int h = 0; h < nsp; ++h) if (label[h] == c) epc[spb[h * 5 + 1] - imin]++;
+        for (cmv = 0, best_i = imin; best_i <= imax; ++best_i) { cmv += epc[best_i - imin]; if ((float)cmv / (float)ninc >= 0.02f) break; }
+        for (int z = 0; z <= jmax - jmin; ++z) epc[z] = 0;
+        for (int h = 0; h < nsp; ++h) if (label[h] == c) epc[spb[h * 5 + 2] - jmin]++;
+        for (cmv = 0, best_j = jmax; best_j >= jmin; --best_j) { cmv += epc[best_j - jmin]; if ((float)cmv / (float)ninc >= 0.02f) break; }
+        if (best_i > best_j) continue;
+        if (nout < MAXENV) { eo[nout].pair = reg.pair; eo[nout].i = best_i; eo[nout].j = best_j; eo[nout].null2_done = 1; eo[nout].scratch_off = 0; nout++; }
+      }
+      // order of occurrence in the target
+      for (int a = 1; a < nout; ++a) { Envelope v = eo[a]; int b = a - 1; while (b >= 0 && eo[b].i > v.i) { eo[b + 1] = eo[b]; --b; } eo[b + 1] = v; }
+      ep.env_count[ri] = nout;
+    }
+    __syncwarp();
+  }
+}
+
+int run_ensembles(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, DomdefParams &p, const std::vector<PairWork> &pairs,
+                  const std::vector<Region> &regs, const std::vector<int> &multi_idx, std::vector<std::vector<Envelope>> &out) {
+  (void)db;
+  cudaStream_t st = e->stream;
+  const int nm = (int)multi_idx.size();
+  std::vector<int64_t> off(nm);
+  int64_t tot = 0;
+  for (int i = 0; i < nm; ++i) {
+    const Region &r = regs[multi_idx[i]];
+    const int64_t Lr = r.j - r.i + 1, M = m->models[pairs[r.pair].model].M, Mpad = ((M + 1) + 31) / 32 * 32 + 32;
+    off[i] = tot;
+    tot += (Lr + 1) * 3 * Mpad + (Lr + 1) * X_NX + 2 * (Lr + 1) + (int64_t)SPCAP * 6 + std::max(Lr, M) + 2 + 256 + 64;
+    tot = (tot + 63) / 64 * 64;
+  }
+  void *d_regs = nullptr, *d_idx = nullptr, *d_off = nullptr, *d_scr = nullptr, *d_env = nullptr, *d_cnt = nullptr;
+  auto cleanup = [&]() { cudaFree(d_regs); cudaFree(d_idx); cudaFree(d_off); cudaFree(d_scr); cudaFree(d_env); cudaFree(d_cnt); };
+#define ENS_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #call); } } while (0)
+  ENS_CUDA(cudaMalloc(&d_regs, sizeof(Region) * regs.size()));
+  ENS_CUDA(cudaMalloc(&d_idx, sizeof(int32_t) * nm));
+  ENS_CUDA(cudaMalloc(&d_off, sizeof(int64_t) * nm));
+  ENS_CUDA(cudaMalloc(&d_scr, sizeof(float) * (size_t)tot));
+  ENS_CUDA(cudaMalloc(&d_env, sizeof(Envelope) * (size_t)nm * MAXENV));
+  ENS_CUDA(cudaMalloc(&d_cnt, sizeof(int32_t) * nm));
+  ENS_CUDA(cudaMemcpyAsync(d_regs, regs.data(), sizeof(Region) * regs.size(), cudaMemcpyHostToDevice, st));
+  ENS_CUDA(cudaMemcpyAsync(d_idx, multi_idx.data(), sizeof(int32_t) * nm, cudaMemcpyHostToDevice, st));
+  ENS_CUDA(cudaMemcpyAsync(d_off, off.data(), sizeof(int64_t) * nm, cudaMemcpyHostToDevice, st));
+  ENS_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int32_t) * nm, st));
+  EnsembleParams ep;
+  ep.d = p; ep.regions = (const Region *)d_regs; ep.multi_idx = (const int32_t *)d_idx; ep.nmulti = nm;
+  ep.scratch_off = (const int64_t *)d_off; ep.scratch = (float *)d_scr; ep.env_out = (Envelope *)d_env; ep.env_count = (int32_t *)d_cnt;
+  const size_t smem = (size_t)FWD_WARPS * 3 * p.row_elems * sizeof(float);
+  ENS_CUDA(cudaFuncSetAttribute(ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::min(e->prop.multiProcessorCount * 4, (nm + FWD_WARPS - 1) / FWD_WARPS);
+  ensemble_kernel<<<grid, FWD_WARPS * 32, smem, st>>>(ep);
+  ENS_CUDA(cudaGetLastError());
+  e->stats.kernel_launches++;
+  std::vector<Envelope> envs((size_t)nm * MAXENV);
+  std::vector<int32_t> cnt(nm);
+  ENS_CUDA(cudaMemcpyAsync(envs.data(), d_env, sizeof(Envelope) * envs.size(), cudaMemcpyDeviceToHost, st));
+  ENS_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(int32_t) * nm, cudaMemcpyDeviceToHost, st));
+  ENS_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < nm; ++i)
+    for (int c = 0; c < cnt[i]; ++c) out[i].push_back(envs[(size_t)i * MAXENV + c]);
+  cleanup();
+  return CKM_OK;
+}
+
+}  // namespace ckm

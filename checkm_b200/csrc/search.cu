@@ -249,6 +249,287 @@ int ckm_filter_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_i
   return CKM_OK;
 }
 
+}  // extern "C"
+
+namespace ckm {
+
+constexpr int X_NX_HOST = 6;
+int run_ensembles(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, DomdefParams &p, const std::vector<PairWork> &pairs,
+                  const std::vector<Region> &regs, const std::vector<int> &multi_idx, std::vector<std::vector<Envelope>> &out);
+
+static std::vector<float> &logsum_table() {
+  static std::vector<float> t;
+  if (t.empty()) { t.resize(16000); for (int i = 0; i < 16000; ++i) t[i] = (float)std::log(1.0 + std::exp((double)-i / 1000.0)); }
+  return t;
+}
+
+struct HostHit { int pair; HitOut h; int first_dom, ndom_slots; };
+
+static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_idx, int32_t nmodels, const int64_t *bin_model_offsets,
+                     const ckm_seqdb *db, double Ecut, double domEcut, ckm_hit **hits_out, int64_t *nhits_out) {
+  if (!e || !m || !db || !hits_out || !nhits_out) { set_error("ckm_search: bad argument"); return CKM_EINVAL; }
+  cudaSetDevice(e->device);
+  cudaStream_t st = e->stream;
+  *hits_out = nullptr; *nhits_out = 0;
+  const int ndb = (int)m->models.size();
+  if (model_idx == nullptr && bin_model_offsets == nullptr) nmodels = ndb;
+  ActiveMasks am; std::vector<int32_t> slot;
+  int rc = build_masks(m, db, model_idx, nmodels, bin_model_offsets, am, slot, st);
+  if (rc) return rc;
+  // query order per bin (for output ordering) and the number of pairs
+  int64_t n_pairs = 0;
+  std::vector<std::vector<int32_t>> qorder(bin_model_offsets ? db->nbins : 1);
+  if (bin_model_offsets) {
+    for (int b = 0; b < db->nbins; ++b) {
+      qorder[b].assign(ndb, -1);
+      for (int64_t i = bin_model_offsets[b]; i < bin_model_offsets[b + 1]; ++i) qorder[b][model_idx[i]] = (int32_t)(i - bin_model_offsets[b]);
+      n_pairs += (int64_t)db->bin_nseq[b] * (bin_model_offsets[b + 1] - bin_model_offsets[b]);
+    }
+  } else {
+    qorder[0] = slot;
+    n_pairs = (int64_t)db->nseq * nmodels;
+  }
+  std::memset(&e->stats, 0, sizeof(e->stats));
+  CKM_CUDA(cudaEventRecord(e->ev[8], st));
+  Stage1 s1; Stage2 s2;
+  if ((rc = run_stage1(e, m, db, am, std::max<int64_t>(n_pairs, 1), s1, nullptr))) return rc;
+  if ((rc = run_stage2(e, m, db, am, s1, s2, nullptr, nullptr, nullptr, nullptr))) return rc;
+  int32_t ctr[CTR_N];
+  unsigned long long cells = 0;
+  CKM_CUDA(cudaMemcpyAsync(ctr, e->d_counters, sizeof(ctr), cudaMemcpyDeviceToHost, st));
+  CKM_CUDA(cudaMemcpyAsync(&cells, s1.cells.p, sizeof(cells), cudaMemcpyDeviceToHost, st));
+  CKM_CUDA(cudaStreamSynchronize(st));
+  if (ctr[CTR_CAND] > s1.cand_cap || ctr[CTR_MSV] > s1.pass_cap || ctr[CTR_BIAS] > s2.cap || ctr[CTR_VIT] > s2.cap || ctr[CTR_FWD] > s2.cap) {
+    set_error("candidate queue overflow in the filter cascade"); return CKM_ECAPACITY;
+  }
+  e->stats.n_pairs = n_pairs; e->stats.n_cells = (int64_t)cells;
+  e->stats.n_ssv_cand = ctr[CTR_CAND]; e->stats.n_past_msv = ctr[CTR_MSV]; e->stats.n_past_bias = ctr[CTR_BIAS];
+  e->stats.n_past_vit = ctr[CTR_VIT]; e->stats.n_past_fwd = ctr[CTR_FWD];
+  const int npairs = ctr[CTR_FWD];
+  std::vector<Candidate> fl((size_t)npairs);
+  if (npairs) CKM_CUDA(cudaMemcpy(fl.data(), s2.fwd_list, sizeof(Candidate) * fl.size(), cudaMemcpyDeviceToHost));
+  std::sort(fl.begin(), fl.end(), [](const Candidate &a, const Candidate &b) { return a.seq != b.seq ? a.seq < b.seq : a.model < b.model; });
+  // free the big cascade buffers before the domain stage
+  s1.cand.alloc(0); s1.pass.alloc(0); s2.b.alloc(0);
+
+  std::vector<PairWork> pairs((size_t)npairs);
+  int64_t rows = 0;
+  for (int i = 0; i < npairs; ++i) {
+    PairWork &pw = pairs[i];
+    pw.seq = fl[i].seq; pw.model = fl[i].model; pw.L = db->len[pw.seq];
+    pw.first_dom = 0; pw.ndom_slots = 0; pw.fwdsc = fl[i].fwdsc; pw.filtersc = fl[i].filtersc; pw.usc = fl[i].usc;
+    pw.row_off = rows; rows += pw.L + 1;
+  }
+  const int nsm = e->prop.multiProcessorCount;
+  DevBuf dpairs, dxf, dxb, dvec, dregions, denvs, ddoms, dhits, dscratch, dtbl;
+  std::vector<DomainOut> doms; std::vector<HitOut> hout((size_t)npairs);
+  std::vector<Envelope> envs;
+  CKM_CUDA(cudaEventRecord(e->ev[6], st));
+  if (npairs > 0) {
+    const size_t rws = (size_t)std::max<int64_t>(rows, 1);
+    if ((rc = dpairs.alloc(sizeof(PairWork) * pairs.size())) || (rc = dxf.alloc(sizeof(float) * rws * X_NX_HOST)) || (rc = dxb.alloc(sizeof(float) * rws * X_NX_HOST)) ||
+        (rc = dvec.alloc(sizeof(float) * rws * 4)) || (rc = dtbl.alloc(sizeof(float) * 16000))) return rc;
+    const int region_cap = npairs * 8 + 1024;
+    if ((rc = dregions.alloc(sizeof(Region) * (size_t)region_cap))) return rc;
+    CKM_CUDA(cudaMemcpyAsync(dpairs.p, pairs.data(), sizeof(PairWork) * pairs.size(), cudaMemcpyHostToDevice, st));
+    CKM_CUDA(cudaMemcpyAsync(dtbl.p, logsum_table().data(), sizeof(float) * 16000, cudaMemcpyHostToDevice, st));
+    CKM_CUDA(cudaMemsetAsync(e->d_counters + CTR_ENV, 0, sizeof(int32_t), st));
+    DomdefParams p{};
+    p.res = db->d_res; p.off = db->d_off; p.nullsc = db->d_nullsc; p.ms = m->d_scalars; p.rfv = m->d_rfv; p.tfv = m->d_tfv;
+    p.pairs = dpairs.as<PairWork>(); p.npairs = npairs;
+    p.xf = dxf.as<float>(); p.xb = dxb.as<float>();
+    p.btot = dvec.as<float>(); p.etot = p.btot + rws; p.mocc = p.etot + rws; p.n2sc = p.mocc + rws;
+    p.regions = dregions.as<Region>(); p.region_count = e->d_counters + CTR_ENV; p.region_cap = region_cap;
+    p.logsum_tbl = dtbl.as<float>();
+    p.row_elems = ((m->maxM + 31) / 32) * 32 + 64;
+    if ((rc = launch_regions(p, std::min(nsm * 4, (npairs + FWD_WARPS - 1) / FWD_WARPS), st))) return rc;
+    e->stats.kernel_launches++;
+    int32_t nreg = 0;
+    CKM_CUDA(cudaMemcpyAsync(&nreg, e->d_counters + CTR_ENV, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CKM_CUDA(cudaStreamSynchronize(st));
+    if (nreg > region_cap) { set_error("region queue overflow"); return CKM_ECAPACITY; }
+    std::vector<Region> regs((size_t)nreg);
+    if (nreg) CKM_CUDA(cudaMemcpy(regs.data(), dregions.p, sizeof(Region) * regs.size(), cudaMemcpyDeviceToHost));
+    std::sort(regs.begin(), regs.end(), [](const Region &a, const Region &b) { return a.pair != b.pair ? a.pair < b.pair : a.i < b.i; });
+    // multi-domain regions are resolved by the stochastic-trace ensemble (run_ensembles), which appends envelopes
+    std::vector<Envelope> extra;
+    std::vector<int> multi_idx;
+    for (int r = 0; r < nreg; ++r) if (regs[r].multi) multi_idx.push_back(r);
+    std::vector<std::vector<Envelope>> multi_envs(multi_idx.size());
+    if (!multi_idx.empty()) {
+      if ((rc = run_ensembles(e, m, db, p, pairs, regs, multi_idx, multi_envs))) return rc;
+    }
+    size_t mi = 0;
+    for (int r = 0; r < nreg; ++r) {
+      if (!regs[r].multi) { envs.push_back(Envelope{regs[r].pair, regs[r].i, regs[r].j, 0, 0}); }
+      else { for (const Envelope &en : multi_envs[mi]) envs.push_back(en); ++mi; }
+    }
+    // domain slots per pair
+    for (size_t i = 0; i < envs.size(); ++i) {
+      PairWork &pw = pairs[envs[i].pair];
+      if (pw.ndom_slots == 0) pw.first_dom = (int32_t)i;
+      pw.ndom_slots++;
+    }
+    doms.resize(envs.size());
+    if (!envs.empty()) {
+      // scratch per envelope: 2 matrices + specials; run in waves under a memory budget
+      std::vector<int64_t> need(envs.size());
+      for (size_t i = 0; i < envs.size(); ++i) {
+        const PairWork &pw = pairs[envs[i].pair];
+        const int64_t Ld = envs[i].j - envs[i].i + 1, Mpad = ((m->models[pw.model].M + 1) + 31) / 32 * 32 + 32;
+        need[i] = 2 * (Ld + 1) * 3 * Mpad + (Ld + 1) * 15 + 64;
+      }
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      const int64_t budget = std::max<int64_t>((int64_t)(free_b / 2 / sizeof(float)), *std::max_element(need.begin(), need.end()));
+      if ((rc = denvs.alloc(sizeof(Envelope) * envs.size())) || (rc = ddoms.alloc(sizeof(DomainOut) * envs.size())) || (rc = dhits.alloc(sizeof(HitOut) * pairs.size()))) return rc;
+      CKM_CUDA(cudaMemcpyAsync(dpairs.p, pairs.data(), sizeof(PairWork) * pairs.size(), cudaMemcpyHostToDevice, st));
+      size_t w0 = 0;
+      int64_t cur_alloc = 0;
+      while (w0 < envs.size()) {
+        size_t w1 = w0; int64_t tot = 0;
+        while (w1 < envs.size() && (w1 == w0 || tot + need[w1] <= budget)) { envs[w1].scratch_off = tot; tot += need[w1]; ++w1; }
+        if (tot > cur_alloc) { if ((rc = dscratch.alloc(sizeof(float) * (size_t)tot))) return rc; cur_alloc = tot; }
+        CKM_CUDA(cudaMemcpyAsync(denvs.as<Envelope>() + w0, envs.data() + w0, sizeof(Envelope) * (w1 - w0), cudaMemcpyHostToDevice, st));
+        p.envs = denvs.as<Envelope>(); p.env_begin = (int32_t)w0; p.env_end = (int32_t)w1; p.scratch = dscratch.as<float>(); p.doms = ddoms.as<DomainOut>();
+        if ((rc = launch_envelopes(p, std::min<int>(nsm * 4, (int)((w1 - w0 + FWD_WARPS - 1) / FWD_WARPS)), st))) return rc;
+        e->stats.kernel_launches++;
+        CKM_CUDA(cudaStreamSynchronize(st));
+        w0 = w1;
+      }
+      p.hits = dhits.as<HitOut>();
+      if ((rc = launch_scores(p, (npairs + 127) / 128, st))) return rc;
+      e->stats.kernel_launches++;
+      CKM_CUDA(cudaMemcpyAsync(doms.data(), ddoms.p, sizeof(DomainOut) * doms.size(), cudaMemcpyDeviceToHost, st));
+      CKM_CUDA(cudaMemcpyAsync(hout.data(), dhits.p, sizeof(HitOut) * hout.size(), cudaMemcpyDeviceToHost, st));
+      CKM_CUDA(cudaStreamSynchronize(st));
+    } else {
+      for (auto &h : hout) std::memset(&h, 0, sizeof(h));
+    }
+  }
+  CKM_CUDA(cudaEventRecord(e->ev[7], st));
+  CKM_CUDA(cudaEventSynchronize(e->ev[7]));
+
+  // ---- thresholds, ordering, rows (bookkeeping on the hit list; hmmsearch's output phase) ----
+  struct Key { int bin, q, pair; double lnP; int seq; };
+  std::vector<Key> keys;
+  for (int i = 0; i < npairs; ++i) {
+    if (!hout[i].valid) continue;
+    const int b = db->bin_of_seq[pairs[i].seq];
+    const int q = (bin_model_offsets ? qorder[b] : qorder[0])[pairs[i].model];
+    keys.push_back(Key{b, q, i, hout[i].lnP, pairs[i].seq});
+  }
+  std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) {
+    if (a.bin != b.bin) return a.bin < b.bin;
+    if (a.q != b.q) return a.q < b.q;
+    if (a.lnP != b.lnP) return a.lnP < b.lnP;
+    return a.seq < b.seq;
+  });
+  std::vector<ckm_hit> rows_out;
+  size_t g0 = 0;
+  int64_t n_dom = 0;
+  for (size_t i = 0; i < doms.size(); ++i) if (doms[i].ok) n_dom++;
+  while (g0 < keys.size()) {
+    size_t g1 = g0;
+    while (g1 < keys.size() && keys[g1].bin == keys[g0].bin && keys[g1].q == keys[g0].q) ++g1;
+    const double Z = (double)db->bin_nseq[keys[g0].bin];
+    double domZ = 0.0;
+    for (size_t k = g0; k < g1; ++k) if (std::exp(keys[k].lnP) * Z <= Ecut) domZ += 1.0;
+    for (size_t k = g0; k < g1; ++k) {
+      if (!(std::exp(keys[k].lnP) * Z <= Ecut)) continue;
+      const PairWork &pw = pairs[keys[k].pair];
+      const HitOut &h = hout[keys[k].pair];
+      int nrep = 0;
+      for (int d = pw.first_dom; d < pw.first_dom + pw.ndom_slots; ++d)
+        if (doms[d].ok && std::exp(doms[d].lnP) * domZ <= domEcut) nrep++;
+      int nd = 0;
+      for (int d = pw.first_dom; d < pw.first_dom + pw.ndom_slots; ++d) {
+        const DomainOut &dm = doms[d];
+        if (!dm.ok || !(std::exp(dm.lnP) * domZ <= domEcut)) continue;
+        ckm_hit r;
+        std::memset(&r, 0, sizeof(r));
+        r.bin = keys[k].bin; r.seq = pw.seq; r.model = pw.model; r.tlen = pw.L; r.qlen = m->models[pw.model].M;
+        r.dom = ++nd; r.ndom = nrep;
+        r.hmm_from = dm.hmmfrom; r.hmm_to = dm.hmmto; r.ali_from = dm.sqfrom; r.ali_to = dm.sqto; r.env_from = dm.ienv; r.env_to = dm.jenv;
+        r.full_score = h.score; r.full_bias = h.pre_score - h.score;
+        r.dom_score = dm.bitscore; r.dom_bias = (float)((double)dm.dombias * 1.44269504088896341);
+        r.acc = (float)(dm.oasc / (1.0 + std::fabs((float)(dm.jenv - dm.ienv))));
+        r.full_evalue = std::exp(h.lnP) * Z; r.c_evalue = std::exp(dm.lnP) * domZ; r.i_evalue = std::exp(dm.lnP) * Z;
+        r.full_lnP = h.lnP; r.dom_lnP = dm.lnP;
+        rows_out.push_back(r);
+      }
+    }
+    g0 = g1;
+  }
+  e->stats.n_hits_seq = (int64_t)keys.size(); e->stats.n_domains = n_dom; e->stats.n_reported = (int64_t)rows_out.size();
+  cudaEventElapsedTime(&e->stats.ms_ssv, e->ev[0], e->ev[1]);
+  cudaEventElapsedTime(&e->stats.ms_msv, e->ev[1], e->ev[2]);
+  cudaEventElapsedTime(&e->stats.ms_bias, e->ev[2], e->ev[3]);
+  cudaEventElapsedTime(&e->stats.ms_vit, e->ev[3], e->ev[4]);
+  cudaEventElapsedTime(&e->stats.ms_fwd, e->ev[4], e->ev[5]);
+  cudaEventElapsedTime(&e->stats.ms_domdef, e->ev[6], e->ev[7]);
+  cudaEventElapsedTime(&e->stats.ms_total, e->ev[8], e->ev[7]);
+  if (!rows_out.empty()) {
+    ckm_hit *out = (ckm_hit *)std::malloc(sizeof(ckm_hit) * rows_out.size());
+    if (!out) { set_error("out of host memory"); return CKM_ENOMEM; }
+    std::memcpy(out, rows_out.data(), sizeof(ckm_hit) * rows_out.size());
+    *hits_out = out;
+  }
+  *nhits_out = (int64_t)rows_out.size();
+  return CKM_OK;
+}
+
+}  // namespace ckm
+
+extern "C" {
+
+int ckm_search(ckm_engine *e, const ckm_models *m, const int32_t *model_idx, int32_t nmodels,
+               const ckm_seqdb *db, double E, double domE, ckm_hit **hits_out, int64_t *nhits_out) {
+  return do_search(e, m, model_idx, nmodels, nullptr, db, E, domE, hits_out, nhits_out);
+}
+
+int ckm_search_per_bin(ckm_engine *e, const ckm_models *m, const int32_t *model_idx, const int64_t *bin_model_offsets,
+                       const ckm_seqdb *db, double E, double domE, ckm_hit **hits_out, int64_t *nhits_out) {
+  if (!model_idx || !bin_model_offsets) { set_error("ckm_search_per_bin: bad argument"); return CKM_EINVAL; }
+  return do_search(e, m, model_idx, 0, bin_model_offsets, db, E, domE, hits_out, nhits_out);
+}
+
+// domtblout writer: the 22 columns + description CheckM's HMMERParser.readHitsDOM splits (checkm/hmmer.py:184-200)
+int ckm_write_domtblout(const ckm_models *m, const ckm_hit *hits, int64_t nhits, int32_t bin, int32_t seq_base,
+                        const char *const *names, const char *const *descs, const char *path) {
+  if (!m || (!hits && nhits > 0) || !names || !path) { set_error("ckm_write_domtblout: bad argument"); return CKM_EINVAL; }
+  FILE *fp = std::fopen(path, "w");
+  if (!fp) { set_error(std::string("cannot write ") + path); return CKM_EIO; }
+  int tnamew = 20, qnamew = 20, qaccw = 10, taccw = 10;
+  for (int64_t i = 0; i < nhits; ++i) {
+    if (hits[i].bin != bin) continue;
+    const Model &md = m->models[hits[i].model];
+    tnamew = std::max<int>(tnamew, (int)std::strlen(names[hits[i].seq - seq_base]));
+    qnamew = std::max<int>(qnamew, (int)md.name.size());
+    qaccw = std::max<int>(qaccw, (int)md.acc.size());
+  }
+  std::fprintf(fp, "#%*s %22s %40s %11s %11s %11s\n", tnamew + qnamew - 1 + 15 + taccw + qaccw, "", "--- full sequence ---",
+               "-------------- this domain -------------", "hmm coord", "ali coord", "env coord");
+  std::fprintf(fp, "#%-*s %-*s %5s %-*s %-*s %5s %9s %6s %5s %3s %3s %9s %9s %6s %5s %5s %5s %5s %5s %5s %5s %4s %s\n",
+               tnamew - 1, " target name", taccw, "accession", "tlen", qnamew, "query name", qaccw, "accession", "qlen",
+               "E-value", "score", "bias", "#", "of", "c-Evalue", "i-Evalue", "score", "bias", "from", "to", "from", "to", "from", "to", "acc", "description of target");
+  std::fprintf(fp, "#%*s %*s ----- %*s %*s ----- --------- ------ ----- --- --- --------- --------- ------ ----- ----- ----- ----- ----- ----- ----- ---- ---------------------\n",
+               tnamew - 1, "-------------------", taccw, "----------", qnamew, "--------------------", qaccw, "----------");
+  for (int64_t i = 0; i < nhits; ++i) {
+    const ckm_hit &h = hits[i];
+    if (h.bin != bin) continue;
+    const Model &md = m->models[h.model];
+    const char *desc = (descs && descs[h.seq - seq_base] && descs[h.seq - seq_base][0]) ? descs[h.seq - seq_base] : "-";
+    std::fprintf(fp, "%-*s %-*s %5d %-*s %-*s %5d %9.2g %6.1f %5.1f %3d %3d %9.2g %9.2g %6.1f %5.1f %5d %5d %5d %5d %5d %5d %4.2f %s\n",
+                 tnamew, names[h.seq - seq_base], taccw, "-", h.tlen, qnamew, md.name.c_str(), qaccw, md.acc.empty() ? "-" : md.acc.c_str(), h.qlen,
+                 h.full_evalue, h.full_score, h.full_bias, h.dom, h.ndom, h.c_evalue, h.i_evalue, h.dom_score, h.dom_bias,
+                 h.hmm_from, h.hmm_to, h.ali_from, h.ali_to, h.env_from, h.env_to, h.acc, desc);
+  }
+  std::fprintf(fp, "#\n# Program:         checkm_b200 (libckm.so)\n# Pipeline mode:   SEARCH\n# [ok]\n");
+  std::fclose(fp);
+  return CKM_OK;
+}
+
 int ckm_msv_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_idx, int32_t nmodels,
                    const ckm_seqdb *db, int32_t *xj_out) {
   if (!e || !m || !db || !xj_out) { set_error("ckm_msv_scores: bad argument"); return CKM_EINVAL; }

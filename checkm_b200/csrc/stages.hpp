@@ -65,4 +65,36 @@ int launch_bias(const FilterParams &p, int grid, cudaStream_t st);
 int launch_vit(const FilterParams &p, int grid, cudaStream_t st);
 int launch_fwd(const FilterParams &p, int grid, cudaStream_t st);
 
+// ---- stage 5: domain definition ----
+#define FLT_MIN_F 1.17549435e-38f
+struct PairWork {          // one pair that passed the Forward filter
+  int32_t seq, model, L;
+  int32_t first_dom, ndom_slots;     // its envelopes/domains occupy doms[first_dom .. first_dom+ndom_slots)
+  float   fwdsc, filtersc, usc;
+  int64_t row_off;                   // offset (in rows of L+1) of its per-residue arrays
+};
+struct Region { int32_t pair, i, j, multi; };
+struct Envelope { int32_t pair, i, j, null2_done; int64_t scratch_off; };
+struct DomainOut {
+  int32_t pair, ienv, jenv, hmmfrom, hmmto, sqfrom, sqto, ok;
+  float   envsc, domcorrection, oasc, bitscore, dombias, pad;
+  double  lnP;
+};
+struct HitOut { float pre_score, score, sum_score; int32_t ndom, valid, pad; double lnP; };
+struct DomdefParams {
+  const uint8_t *res; const int64_t *off; const float *nullsc;
+  const ModelScalars *ms; const float *rfv; const float *tfv;
+  const PairWork *pairs; int32_t npairs;
+  float *xf, *xb, *btot, *etot, *mocc, *n2sc;      // per-pair arrays, indexed by row_off
+  Region *regions; int32_t *region_count; int32_t region_cap;
+  const Envelope *envs; int32_t env_begin, env_end;
+  float *scratch;
+  DomainOut *doms; HitOut *hits;
+  const float *logsum_tbl;
+  int32_t row_elems;
+};
+int launch_regions(const DomdefParams &p, int grid, cudaStream_t st);
+int launch_envelopes(const DomdefParams &p, int grid, cudaStream_t st);
+int launch_scores(const DomdefParams &p, int grid, cudaStream_t st);
+
 }  // namespace ckm

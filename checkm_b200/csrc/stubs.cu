@@ -1,12 +1,12 @@
 // stubs.cu -- entry points still under construction; they fail loudly rather than fall back.
+#include <vector>
 #include "engine.hpp"
+#include "stages.hpp"
 using namespace ckm;
 extern "C" {
 int ckm_allgather_qa(ckm_engine *, void *, const ckm_qa_row *, int32_t, int32_t, int32_t, ckm_qa_row *, int32_t *) { set_error("ckm_allgather_qa: not implemented yet"); return CKM_EINVAL; }
 }
 extern "C" {
-int ckm_search(ckm_engine *, const ckm_models *, const int32_t *, int32_t, const ckm_seqdb *, double, double, ckm_hit **, int64_t *) { set_error("ckm_search: not implemented yet"); return CKM_EINVAL; }
-int ckm_search_per_bin(ckm_engine *, const ckm_models *, const int32_t *, const int64_t *, const ckm_seqdb *, double, double, ckm_hit **, int64_t *) { set_error("ckm_search_per_bin: not implemented yet"); return CKM_EINVAL; }
-int ckm_write_domtblout(const ckm_models *, const ckm_hit *, int64_t, int32_t, int32_t, const char *const *, const char *const *, const char *) { set_error("ckm_write_domtblout: not implemented yet"); return CKM_EINVAL; }
 int ckm_reduce(ckm_engine *, const ckm_models *, const ckm_seqdb *, const ckm_hit *, int64_t, const ckm_reduce_opts *, const ckm_reduce_meta *, ckm_qa_row **, int32_t *, ckm_marker_hit **, int64_t *) { set_error("ckm_reduce: not implemented yet"); return CKM_EINVAL; }
 }
+
