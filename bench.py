@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- genomes/hour of the marker-gene search hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+Workload (config["workload"]): BASELINE.json configs[2] stand-in -- synthetic 3 Mb bins (2,900 ORFs, ~0.9 M residues,
+SURVEY.md 8d) x a 5,000-model HMM database (the 43 real CPR models + 4,957 models stitched from their rows, lengths
+log-normal around 240).  One "step" = the whole hot path (SSV/MSV -> bias -> Viterbi -> Forward -> domain definition ->
+hit table -> marker-set reduction) over one batch of `bins_per_step` bins.  With N > 1 every rank searches its own bins
+(weak scaling, no data-path collective) and the per-bin QA rows are all-gathered over NCCL at the end of each step.
+
+value : inputs (digitised ORFs, models) resident in HBM before the timed region.
+e2e   : the same through the public API with HOST buffers -- H2D of the step's residues and D2H of its hit table and QA
+        rows inside the timed region.
+--impl reference : the CPU restatement of HMMER3's pipeline (oracle/, "port") on all host cores, a bounded sample/step.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+CPR = os.path.join(ROOT, 'tests', 'golden', 'cpr_43_markers.hmm')
+
+N_MODELS = 5000
+ORFS_PER_BIN = 2900
+BINS_PER_STEP = 4
+
+
+def rank_info():
+    return int(os.environ.get('RANK', '0')), int(os.environ.get('LOCAL_RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+
+
+def model_db(tag=''):
+    """5,000-model database file (43 real + synthetic), written once per box under /tmp."""
+    from checkm_b200 import synth
+    path = '/tmp/ckm_bench_db_%d%s.hmm' % (N_MODELS, tag)
+    plant = '/tmp/ckm_bench_plant%s.hmm' % tag
+    if not (os.path.exists(path) and os.path.exists(plant)):
+        rng = np.random.default_rng(20260923)
+        lens = synth.perturbed_model_lengths(rng, N_MODELS - 43)
+        tmp = path + '.%d.tmp' % os.getpid()
+        synth.make_model_db_fast(tmp, CPR, lens, seed=1)
+        with open(tmp + '2', 'w') as out:
+            out.write(open(CPR).read())
+            out.write(open(tmp).read())
+        os.remove(tmp)
+        os.replace(tmp + '2', path)
+        # the first 160 synthetic models again, alone, to plant homologs from
+        with open(path) as f, open(plant + '.tmp', 'w') as out:
+            n = 0
+            for line in f:
+                out.write(line)
+                if line.startswith('//'):
+                    n += 1
+                    if n >= 43 + 160:
+                        break
+        os.replace(plant + '.tmp', plant)
+    return path, plant
+
+
+def make_bins(plant_path, n, seed0):
+    from checkm_b200 import synth
+    hm = synth.read_hmms(plant_path)
+    bins = [synth.make_bin('bin%d' % (seed0 + i), hm, seed=seed0 + i, n_orfs=ORFS_PER_BIN, copies=(0, 1, 1, 1, 2)) for i in range(n)]
+    res = np.concatenate([b.residues for b in bins])
+    lens = np.concatenate([np.diff(b.offsets) for b in bins])
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(lens)
+    binof = np.concatenate([np.full(b.nseq, i, np.int32) for i, b in enumerate(bins)])
+    return bins, res, off, binof
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return json.load(open(p)), 'measured'
+    return {"hbm_gbs": 6650.0}, 'fallback'
+
+
+def oracle_sample(db_path, bins, nthreads, n_models=64):
+    """CPU restatement on a bounded sample: bin 0 x the first `n_models` models; returns (seconds, sum M of the sample)."""
+    from oracle import pyoracle as po
+    sub = '/tmp/ckm_bench_cpu_sample_%d.hmm' % n_models
+    if not os.path.exists(sub):
+        with open(db_path) as f, open(sub + '.tmp', 'w') as out:
+            n = 0
+            for line in f:
+                out.write(line)
+                if line.startswith('//'):
+                    n += 1
+                    if n >= n_models:
+                        break
+        os.replace(sub + '.tmp', sub)
+    hf = po.HmmFile(sub)
+    b = bins[0]
+    t0 = time.perf_counter()
+    rp = po.search(hf, b.residues, b.offsets, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    nh = rp.contents.nhits
+    po.free_results(rp)
+    return dt, sum(h.M for h in hf.headers), nh
+
+
+def total_model_positions(db_path):
+    tot = 0
+    with open(db_path) as f:
+        for line in f:
+            if line.startswith('LENG'):
+                tot += int(line.split()[1])
+    return tot
+
+
+def run_reference(args):
+    rank, local, world = rank_info()
+    if rank != 0:
+        return
+    db_path, plant = model_db()
+    bins, _, _, _ = make_bins(plant, 1, 1000)
+    cores = os.cpu_count() or 1
+    sumM_all = total_model_positions(db_path)
+    for _ in range(max(args.warmup, 0) and 1):
+        oracle_sample(db_path, bins, cores, n_models=16)
+    t = 0.0
+    sumM = 0
+    for _ in range(args.steps):
+        dt, sumM, _ = oracle_sample(db_path, bins, cores, n_models=48)
+        t += dt
+    per_bin = (t / args.steps) * (sumM_all / float(sumM))        # seconds to search one bin against all 5,000 models
+    gph = 3600.0 / per_bin
+    sample = "1 bin (%d ORFs) x first 48 of %d models per step, scaled by model positions (%d of %d)" % (ORFS_PER_BIN, N_MODELS, sumM, sumM_all)
+    line = {"metric": "genomes/hour", "value": gph, "unit": "genomes/hour", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int16/f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": "configs[2] stand-in: synthetic 3 Mb bins x 5,000 HMMs (43 real CPR + 4,957 stitched)", "bins_per_step": 1,
+                       "orfs_per_bin": ORFS_PER_BIN, "n_models": N_MODELS},
+            "cpu_baseline": {"value": gph, "unit": "genomes/hour", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": gph, "unit": "genomes/hour", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ckm')
+    ap.add_argument('--bins-per-step', type=int, default=BINS_PER_STEP)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+        return
+    rank, local, world = rank_info()
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    os.environ['CKM_DEVICE'] = str(local)
+    from checkm_b200 import _lib, runtime
+    from checkm_b200.resultsParser import QA_DTYPE
+    B = args.bins_per_step
+    if rank == 0:
+        db_path, plant = model_db()
+    if world > 1:
+        dist.barrier()
+    db_path, plant = model_db()
+    eng = runtime.engine()
+    t0 = time.perf_counter()
+    models = runtime.models_for(db_path)
+    t_load = time.perf_counter() - t0
+    info = models.info()
+    sumM_all = sum(int(mi.M) for mi in info)
+    # two alternating batches of bins per rank, distinct across ranks
+    batches = []
+    for z in range(2):
+        bins, res, off, binof = make_bins(plant, B, 10000 * (rank + 1) + 100 * z)
+        batches.append(dict(bins=bins, res=res, off=off, binof=binof, db=eng.seqdb(res, off, binof, B)))
+    # reduction metadata: one marker set per bin = all models (HMM-file semantics), no clans
+    nm = models.n
+    acc_is_tigr = np.asarray([1 if b'TIGR' in mi.acc else 0 for mi in info], dtype=np.uint8)
+    is_pfam = np.asarray([1 if mi.acc.startswith(b'PF') else 0 for mi in info], dtype=np.uint8)
+    clan = np.full(nm, -1, dtype=np.int32)
+    nest_off = np.zeros(nm + 1, dtype=np.int64)
+    has = np.zeros((nm, 3), dtype=np.int32)
+    cut = np.zeros((nm, 6), dtype=np.float64)
+    for i, mi in enumerate(info):
+        has[i] = (mi.has_ga, mi.has_tc, mi.has_nc)
+        cut[i] = (mi.ga_d[0], mi.ga_d[1], mi.tc_d[0], mi.tc_d[1], mi.nc_d[0], mi.nc_d[1])
+    opts = _lib.ReduceOpts()
+    opts.evalue_threshold, opts.evalue_exp10, opts.evalue_mant = 1e-10, -10, 10.0
+    opts.length_threshold, opts.pseudogene_length = 0.7, 0.3
+    bin_set_off = np.arange(B + 1, dtype=np.int64)
+    set_marker_off = (np.arange(B + 1, dtype=np.int64) * nm)
+    set_marker_idx = np.tile(np.arange(nm, dtype=np.int32), B)
+
+    def reduce_hits(batch, hits):
+        names = [n for b in batch['bins'] for n in b.names]
+        key = id(batch)
+        if key not in reduce_hits.cache:
+            scaf, num, rank_ = [], [], []
+            base = 0
+            for bi, b in enumerate(batch['bins']):
+                order = {n: r for r, n in enumerate(sorted(b.names))}
+                for n in b.names:
+                    c = n.rfind('_')
+                    scaf.append(hash((bi, n[:c])) & 0x7fffffff)
+                    num.append(int(n[c + 1:]))
+                    rank_.append(order[n])
+            reduce_hits.cache[key] = tuple(np.asarray(a, dtype=np.int32) for a in (scaf, num, rank_))
+        scaf, num, rank_ = reduce_hits.cache[key]
+        meta = _lib.ReduceMeta()
+        meta.is_pfam, meta.is_tigr, meta.clan = is_pfam.ctypes.data, acc_is_tigr.ctypes.data, clan.ctypes.data
+        meta.nest_off, meta.nest_idx = nest_off.ctypes.data, None
+        meta.has_cut, meta.cutoffs = has.ctypes.data, cut.ctypes.data
+        meta.scaffold_id, meta.orf_num, meta.name_rank = scaf.ctypes.data, num.ctypes.data, rank_.ctypes.data
+        meta.bin_set_off, meta.set_marker_off, meta.set_marker_idx = bin_set_off.ctypes.data, set_marker_off.ctypes.data, set_marker_idx.ctypes.data
+        qa = C.POINTER(_lib.QaRow)()
+        nqa = C.c_int32()
+        mh = C.POINTER(_lib.MarkerHit)()
+        nmh = C.c_int64()
+        harr = np.ascontiguousarray(hits)
+        _lib.check(_lib.lib().ckm_reduce(eng._h, nm, len(names), B, harr.ctypes.data_as(C.POINTER(_lib.Hit)), len(harr), C.byref(opts),
+                                         C.byref(meta), C.byref(qa), C.byref(nqa), C.byref(mh), C.byref(nmh)))
+        buf = (C.c_char * (nqa.value * C.sizeof(_lib.QaRow))).from_address(C.addressof(qa.contents))
+        rows = np.frombuffer(buf, dtype=QA_DTYPE).copy()
+        _lib.lib().ckm_free(qa)
+        _lib.lib().ckm_free(mh)
+        return rows, nmh.value
+    reduce_hits.cache = {}
+
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
+    gather_buf = torch.empty((world, B * QA_DTYPE.itemsize), dtype=torch.uint8, device='cuda') if world > 1 else None
+
+    def gather(rows):
+        if world == 1:
+            return rows
+        mine = torch.from_numpy(rows.view(np.uint8).copy()).cuda()
+        dist.all_gather_into_tensor(gather_buf.view(-1), mine)        # NCCL all-gather of the fixed-width QA rows (config #4)
+        return gather_buf
+
+    def step_resident(i):
+        batch = batches[i % 2]
+        flush_buf.zero_()
+        hits = eng.search(models, batch['db'])
+        st = eng.stats()
+        rows, nmh = reduce_hits(batch, hits)
+        gather(rows)
+        return hits, st, rows
+
+    def step_e2e(i):
+        batch = batches[i % 2]
+        flush_buf.zero_()
+        db = eng.seqdb(batch['res'], batch['off'], batch['binof'], B)       # host buffers -> HBM
+        try:
+            hits = eng.search(models, db)                                   # hit table back on the host
+        finally:
+            db.close()
+        rows, nmh = reduce_hits(batch, hits)
+        gather(rows)
+        return hits, rows
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local)
+    sampler.start()
+    sync()
+    t0 = time.perf_counter()
+    ssv_ms = msv_ms = other_ms = 0.0
+    launches = cells = pairs = resid_sum = 0
+    last = None
+    for i in range(args.steps):
+        hits, st, rows = step_resident(i)
+        ssv_ms += st.ms_ssv
+        msv_ms += st.ms_msv
+        other_ms += st.ms_bias + st.ms_vit + st.ms_fwd + st.ms_domdef
+        launches += st.kernel_launches + 5
+        cells += st.n_cells
+        pairs += st.n_pairs
+        last = (hits, st, rows)
+    sync()
+    t_res = time.perf_counter() - t0
+    sync()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        hits_e, rows_e = step_e2e(i)
+    sync()
+    t_e2e = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    if world > 1:
+        tt = torch.tensor([t_res, t_e2e], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_res, t_e2e = float(tt[0]), float(tt[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hits, st, rows = last
+    genomes = B * args.steps * world
+    value = genomes / t_res * 3600.0
+    e2e = genomes / t_e2e * 3600.0
+    # roofline of the dominant kernel (SSV pre-filter): algorithmic bytes = sum over pairs of (L + 4)
+    resid = float(sum(len(b['res']) for b in batches[:1]))
+    alg_bytes_per_step = resid * nm + 4.0 * (pairs / args.steps)
+    peaks, peak_kind = measured_peaks()
+    ssv_s = (ssv_ms / args.steps) / 1000.0
+    achieved = alg_bytes_per_step / ssv_s / 1e9
+    real_cells = resid * sumM_all
+    h2d = int(batches[0]['db'].residues.nbytes + batches[0]['off'].nbytes + batches[0]['binof'].nbytes)
+    d2h = int(hits.nbytes + rows.nbytes)
+    line = {"metric": "genomes/hour", "value": value, "unit": "genomes/hour", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16 (SSV) / u8 (MSV) / int16 (Viterbi) / f32 (Forward, domain definition)", "data": "synthetic",
+            "config": {"workload": "configs[2] stand-in: synthetic 3 Mb bins (2,900 ORFs, ~0.9 M residues) x 5,000 HMMs (43 real CPR + 4,957 stitched, sum M = %d)" % sumM_all,
+                       "bins_per_step": B, "orfs_per_bin": ORFS_PER_BIN, "n_models": nm, "per_gpu_bins_per_step": B, "parallelism": "bins sharded, 1 process/GPU",
+                       "l2": "256 MiB flush write before every step", "model_load_s": t_load},
+            "e2e": {"value": e2e, "unit": "genomes/hour", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": achieved / peaks.get("hbm_gbs"),
+                         "traffic": None, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == 'measured' else 'fallback 6650',
+                         "kernel": "ssv_kernel<J> (SSV pre-filter, all pairs)", "kernel_ms_per_step": ssv_ms / args.steps,
+                         "note": "the stage is DP-cell bound, not HBM bound (SURVEY.md 8d): see gcups"},
+            "gcups": {"real_cells_per_step": real_cells, "tile_cells_per_step": cells / args.steps, "ssv_gcups_real": real_cells / ssv_s / 1e9,
+                      "ssv_gcups_tile": cells / args.steps / ssv_s / 1e9, "smem_bound_gcups_at_1.9GHz": 148 * 51.2 * 1.9,
+                      "stage_ms_per_step": {"ssv": ssv_ms / args.steps, "msv_exact": msv_ms / args.steps, "bias+vit+fwd+domdef": other_ms / args.steps}},
+            "cascade": {"pairs": int(st.n_pairs), "ssv_cand": int(st.n_ssv_cand), "past_msv": int(st.n_past_msv), "past_bias": int(st.n_past_bias),
+                        "past_vit": int(st.n_past_vit), "past_fwd": int(st.n_past_fwd), "rows": int(st.n_reported)},
+            "clocks": sampler.summary()}
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        dt, sumM, _ = oracle_sample(db_path, batches[0]['bins'], cores, n_models=48)
+        per_bin = dt * (sumM_all / float(sumM))
+        line["cpu_baseline"] = {"value": 3600.0 / per_bin, "unit": "genomes/hour", "cores": cores, "kind": "port",
+                                "sample": "1 bin x first 48 of %d models (%d of %d model positions), %.1f s, scaled" % (nm, sumM, sumM_all, dt)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

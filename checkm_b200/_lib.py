@@ -10,7 +10,8 @@ LIB_PATH = os.path.join(_HERE, "libckm.so")
 class ModelInfo(C.Structure):
     _fields_ = [("name", C.c_char * 128), ("acc", C.c_char * 64), ("desc", C.c_char * 256), ("M", C.c_int32),
                 ("has_ga", C.c_int32), ("has_tc", C.c_int32), ("has_nc", C.c_int32),
-                ("ga", C.c_float * 2), ("tc", C.c_float * 2), ("nc", C.c_float * 2), ("evparam", C.c_float * 6)]
+                ("ga", C.c_float * 2), ("tc", C.c_float * 2), ("nc", C.c_float * 2), ("evparam", C.c_float * 6),
+                ("ga_d", C.c_double * 2), ("tc_d", C.c_double * 2), ("nc_d", C.c_double * 2)]
 
 
 class Hit(C.Structure):
@@ -43,18 +44,19 @@ class MarkerHit(C.Structure):
     _fields_ = [("bin", C.c_int32), ("model", C.c_int32), ("seq_a", C.c_int32), ("seq_b", C.c_int32),
                 ("target_length", C.c_int32), ("hmm_from", C.c_int32), ("hmm_to", C.c_int32),
                 ("ali_from", C.c_int32), ("ali_to", C.c_int32), ("env_from", C.c_int32), ("env_to", C.c_int32),
-                ("order", C.c_int32), ("src_row", C.c_int32)]
+                ("order", C.c_int32), ("src_row", C.c_int32), ("dict_key", C.c_int64)]
 
 
 class ReduceOpts(C.Structure):
     _fields_ = [("ignore_thresholds", C.c_int32), ("skip_pseudogene", C.c_int32), ("skip_adjacent", C.c_int32),
-                ("individual_markers", C.c_int32), ("evalue_threshold", C.c_double), ("length_threshold", C.c_double),
+                ("individual_markers", C.c_int32), ("evalue_threshold", C.c_double), ("evalue_exp10", C.c_int32),
+                ("pad0", C.c_int32), ("evalue_mant", C.c_double), ("length_threshold", C.c_double),
                 ("pseudogene_length", C.c_double)]
 
 
 class ReduceMeta(C.Structure):
     _fields_ = [("is_pfam", C.c_void_p), ("is_tigr", C.c_void_p), ("clan", C.c_void_p),
-                ("nest_off", C.c_void_p), ("nest_idx", C.c_void_p),
+                ("nest_off", C.c_void_p), ("nest_idx", C.c_void_p), ("has_cut", C.c_void_p), ("cutoffs", C.c_void_p),
                 ("scaffold_id", C.c_void_p), ("orf_num", C.c_void_p), ("name_rank", C.c_void_p),
                 ("bin_set_off", C.c_void_p), ("set_marker_off", C.c_void_p), ("set_marker_idx", C.c_void_p)]
 
@@ -64,7 +66,7 @@ SYMBOLS = ["ckm_init", "ckm_destroy", "ckm_last_error", "ckm_version", "ckm_devi
            "ckm_models_load", "ckm_models_count", "ckm_models_info", "ckm_models_find", "ckm_models_select",
            "ckm_models_write", "ckm_models_free", "ckm_digitize", "ckm_seqdb_create", "ckm_seqdb_free",
            "ckm_search", "ckm_search_per_bin", "ckm_hits_free", "ckm_last_stats", "ckm_msv_scores",
-           "ckm_filter_scores", "ckm_write_domtblout", "ckm_reduce", "ckm_free", "ckm_allgather_qa"]
+           "ckm_filter_scores", "ckm_write_domtblout", "ckm_reduce", "ckm_genome_check", "ckm_free", "ckm_allgather_qa"]
 
 _lib = None
 
@@ -105,9 +107,10 @@ def lib():
     L.ckm_filter_scores.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp]
     L.ckm_write_domtblout.argtypes = [vp, C.POINTER(Hit), i64, i32, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p),
                                       C.c_char_p]
-    L.ckm_reduce.argtypes = [vp, vp, vp, C.POINTER(Hit), i64, C.POINTER(ReduceOpts), C.POINTER(ReduceMeta),
+    L.ckm_reduce.argtypes = [vp, i32, i32, i32, C.POINTER(Hit), i64, C.POINTER(ReduceOpts), C.POINTER(ReduceMeta),
                              C.POINTER(C.POINTER(QaRow)), C.POINTER(i32), C.POINTER(C.POINTER(MarkerHit)),
                              C.POINTER(i64)]
+    L.ckm_genome_check.argtypes = [vp, i32, vp, vp, vp, i32, vp]
     L.ckm_free.argtypes = [vp]
     L.ckm_free.restype = None
     L.ckm_allgather_qa.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]

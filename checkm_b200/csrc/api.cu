@@ -97,7 +97,7 @@ int ckm_models_info(const ckm_models *m, int idx, ckm_model_info *out) {
   std::strncpy(out->desc, md.desc.c_str(), sizeof(out->desc) - 1);
   out->M = md.M;
   out->has_ga = md.has_ga; out->has_tc = md.has_tc; out->has_nc = md.has_nc;
-  for (int z = 0; z < 2; ++z) { out->ga[z] = md.ga[z]; out->tc[z] = md.tc[z]; out->nc[z] = md.nc[z]; }
+  for (int z = 0; z < 2; ++z) { out->ga[z] = md.ga[z]; out->tc[z] = md.tc[z]; out->nc[z] = md.nc[z]; out->ga_d[z] = md.ga_d[z]; out->tc_d[z] = md.tc_d[z]; out->nc_d[z] = md.nc_d[z]; }
   for (int z = 0; z < 6; ++z) out->evparam[z] = md.evparam[z];
   return CKM_OK;
 }

@@ -91,9 +91,9 @@ std::vector<Model> read_hmm_file(const std::string &path) {
       else if (tag == "ACC") m.acc = rest_after_tag(line);
       else if (tag == "DESC") m.desc = rest_after_tag(line);
       else if (tag == "LENG") m.M = std::atoi(w.at(1).c_str());
-      else if (tag == "GA" && w.size() >= 3) { m.ga[0] = (float)std::atof(w[1].c_str()); m.ga[1] = (float)std::atof(w[2].c_str()); m.has_ga = true; }
-      else if (tag == "TC" && w.size() >= 3) { m.tc[0] = (float)std::atof(w[1].c_str()); m.tc[1] = (float)std::atof(w[2].c_str()); m.has_tc = true; }
-      else if (tag == "NC" && w.size() >= 3) { m.nc[0] = (float)std::atof(w[1].c_str()); m.nc[1] = (float)std::atof(w[2].c_str()); m.has_nc = true; }
+      else if (tag == "GA" && w.size() >= 3) { for (int z = 0; z < 2; ++z) { m.ga_d[z] = std::atof(w[1 + z].c_str()); m.ga[z] = (float)m.ga_d[z]; } m.has_ga = true; }
+      else if (tag == "TC" && w.size() >= 3) { for (int z = 0; z < 2; ++z) { m.tc_d[z] = std::atof(w[1 + z].c_str()); m.tc[z] = (float)m.tc_d[z]; } m.has_tc = true; }
+      else if (tag == "NC" && w.size() >= 3) { for (int z = 0; z < 2; ++z) { m.nc_d[z] = std::atof(w[1 + z].c_str()); m.nc[z] = (float)m.nc_d[z]; } m.has_nc = true; }
       else if (tag == "STATS" && w.size() >= 5) {
         float a = (float)std::atof(w[3].c_str()), b = (float)std::atof(w[4].c_str());
         if (w[2] == "MSV") { m.evparam[0] = a; m.evparam[1] = b; }

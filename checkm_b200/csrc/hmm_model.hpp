@@ -27,6 +27,7 @@ struct Model {
   int M = 0;
   bool has_ga = false, has_tc = false, has_nc = false, has_compo = false;
   float ga[2] = {0, 0}, tc[2] = {0, 0}, nc[2] = {0, 0};
+  double ga_d[2] = {0, 0}, tc_d[2] = {0, 0}, nc_d[2] = {0, 0};   // as Python's float() reads them (hmmerModelParser.py:76)
   float evparam[6] = {0, 0, 0, 0, 0, 0};
   float compo[K];
   std::vector<float> mat, ins, t;      // probabilities: (M+1)*20, (M+1)*20, (M+1)*7

@@ -7,6 +7,5 @@ extern "C" {
 int ckm_allgather_qa(ckm_engine *, void *, const ckm_qa_row *, int32_t, int32_t, int32_t, ckm_qa_row *, int32_t *) { set_error("ckm_allgather_qa: not implemented yet"); return CKM_EINVAL; }
 }
 extern "C" {
-int ckm_reduce(ckm_engine *, const ckm_models *, const ckm_seqdb *, const ckm_hit *, int64_t, const ckm_reduce_opts *, const ckm_reduce_meta *, ckm_qa_row **, int32_t *, ckm_marker_hit **, int64_t *) { set_error("ckm_reduce: not implemented yet"); return CKM_EINVAL; }
 }
 

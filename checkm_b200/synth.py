@@ -268,3 +268,71 @@ def make_model_db(path, src_path, lengths, seed=0, prefix='SYN'):
         out.append(resample_model(src, int(M), rng, '%s%05d' % (prefix, i), 'PF%05d.1' % (90000 + i) if i % 2 == 0 else 'TIGR%05d' % (90000 + i)))
     write_hmms(path, out)
     return out
+
+
+def make_model_db_fast(path, src_path, lengths, seed=0, prefix='SYN'):
+    """Like make_model_db but stitches the source file's own text lines (no number formatting): fast enough to
+    write the ~5,000-model stand-in of configs #3-#5 in seconds.  Returns the list of model lengths written."""
+    rng = np.random.default_rng(seed)
+    with open(src_path) as f:
+        text = f.read().split('\n')
+    # index the source: per model, header STATS lines and the three text lines of every node
+    src = []
+    i = 0
+    while i < len(text):
+        if not text[i].startswith('HMMER3'):
+            i += 1
+            continue
+        M = 0
+        stats = []
+        while not text[i].startswith('HMM '):
+            if text[i].startswith('LENG'):
+                M = int(text[i].split()[1])
+            elif text[i].startswith('STATS'):
+                stats.append(text[i])
+            i += 1
+        hdr2 = text[i:i + 2]
+        i += 2
+        compo = None
+        if text[i].lstrip().startswith('COMPO'):
+            compo = text[i]
+            i += 1
+        node0 = text[i:i + 2]
+        i += 2
+        nodes = []
+        for k in range(1, M + 1):
+            m_line = text[i]
+            nodes.append((m_line[m_line.index(str(k)) + len(str(k)):][:181], text[i + 1], text[i + 2]))
+            i += 3
+        src.append(dict(M=M, stats=stats, hdr2=hdr2, compo=compo, node0=node0, nodes=nodes))
+        i += 1
+    out = []
+    with open(path, 'w') as f:
+        for n, M in enumerate(lengths):
+            M = int(M)
+            first = src[int(rng.integers(len(src)))]
+            f.write('HMMER3/f [3.1b2 | February 2015]\nNAME  %s%05d\n' % (prefix, n))
+            f.write('ACC   %s\n' % ('PF%05d.1' % (90000 + n) if n % 2 == 0 else 'TIGR%05d' % (90000 + n)))
+            f.write('LENG  %d\nALPH  amino\nRF    no\nMM    no\nCONS  no\nCS    no\nMAP   no\nNSEQ  10\nEFFN  1.000000\nCKSUM 0\n' % M)
+            mu = -8.0 - 0.9 * np.log2(max(M, 2) / 50.0)
+            f.write('STATS LOCAL MSV      %8.4f  0.71000\nSTATS LOCAL VITERBI  %8.4f  0.71000\nSTATS LOCAL FORWARD   -4.0000  0.71000\n' % (mu, mu - 0.6))
+            f.write(first['hdr2'][0] + '\n' + first['hdr2'][1] + '\n')
+            if first['compo'] is not None:
+                f.write(first['compo'] + '\n')
+            f.write(first['node0'][0] + '\n' + first['node0'][1] + '\n')
+            k = 1
+            buf = []
+            while k <= M:
+                s = src[int(rng.integers(len(src)))]
+                w = int(min(M - k + 1, rng.integers(10, 60), s['M'] - 2))
+                a = int(rng.integers(0, s['M'] - w - 1))
+                for z in range(w):
+                    ml, il, tl = s['nodes'][a + z]
+                    if k + z == M:
+                        tl = src[0]['nodes'][-1][2]          # a proper last node: no exits into insert/delete
+                    buf.append('%7d%s\n%s\n%s\n' % (k + z, ml, il, tl))
+                k += w
+            f.write(''.join(buf))
+            f.write('//\n')
+            out.append(M)
+    return out

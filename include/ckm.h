@@ -50,6 +50,7 @@ typedef struct {
   int32_t has_ga, has_tc, has_nc;
   float  ga[2], tc[2], nc[2];
   float  evparam[6];    /* MSV mu, lambda; VITERBI mu, lambda; FORWARD tau, lambda */
+  double ga_d[2], tc_d[2], nc_d[2];   /* the cutoffs as Python's float() reads the header text (hmmerModelParser.py:76) */
 } ckm_model_info;
 
 /* ---- one reported domain = one domtblout row (checkm/hmmer.py:255-285 field for field) ---- */
@@ -99,6 +100,9 @@ typedef struct {
   int32_t hmm_from, hmm_to, ali_from, ali_to, env_from, env_to;
   int32_t order;              /* position within markerHits[acc] for this bin                               */
   int32_t src_row;            /* index of the ckm_hit row that carries this hit's scores / E-values        */
+  int64_t dict_key;           /* orders the markers of a bin as the reference's markerHits dict iterates them:
+                                 -1 for non-Pfam markers (they keep file order and come first, pfam.py:93-100), else the
+                                 position at which the clan filter re-inserted the marker (pfam.py:141-145)       */
 } ckm_marker_hit;
 
 /* ---- lifecycle ---- */
@@ -163,6 +167,9 @@ typedef struct {
   int32_t skip_adjacent;            /* bSkipAdjCorrection                                  */
   int32_t individual_markers;       /* bIndividualMarkers                                  */
   double  evalue_threshold;         /* DefaultValues.E_VAL = 1e-10                         */
+  int32_t evalue_exp10;             /* the same threshold as mant x 10^(exp10-1), 10 <= mant < 100, decomposed */
+  int32_t pad0;                     /*   exactly (decimal) by the caller: the reference compares the 2-digit    */
+  double  evalue_mant;              /*   text of the E-value (hmmer.py:268) against it                         */
   double  length_threshold;         /* DefaultValues.LENGTH = 0.7                          */
   double  pseudogene_length;        /* DefaultValues.PSEUDOGENE_LENGTH = 0.3               */
 } ckm_reduce_opts;
@@ -181,16 +188,25 @@ typedef struct {
   const uint8_t *is_pfam, *is_tigr;
   const int32_t *clan;
   const int64_t *nest_off; const int32_t *nest_idx;
-  const int32_t *scaffold_id, *orf_num;          /* per sequence of the seqdb */
+  const int32_t *has_cut;                        /* nmodels x {ga, tc, nc}: cutoff present                          */
+  const double  *cutoffs;                        /* nmodels x {ga0, ga1, tc0, tc1, nc0, nc1} as float() reads them  */
+  const int32_t *scaffold_id, *orf_num;          /* per sequence */
   const int32_t *name_rank;                      /* per sequence: rank of the name in string order (for "A&&B") */
-  const int64_t *bin_set_off;                    /* nbins+1: sets of bin b are [bin_set_off[b], bin_set_off[b+1]) */
+  const int64_t *bin_set_off;                    /* optional: nbins+1; sets of bin b are [bin_set_off[b], bin_set_off[b+1]) */
   const int64_t *set_marker_off;                 /* nsets+1 */
   const int32_t *set_marker_idx;                 /* model indices */
 } ckm_reduce_meta;
 
-int  ckm_reduce(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, const ckm_hit *hits, int64_t nhits,
+/* hits: domtblout rows grouped by bin (ascending) and, inside a bin, by query (rows of one query contiguous, in file
+ * order).  `model` and `seq` index the caller's model table (nmodels entries) and sequence table (nseq entries). */
+int  ckm_reduce(ckm_engine *e, int32_t nmodels, int32_t nseq, int32_t nbins, const ckm_hit *hits, int64_t nhits,
                 const ckm_reduce_opts *opts, const ckm_reduce_meta *meta,
                 ckm_qa_row **qa_out, int32_t *nqa_out, ckm_marker_hit **mh_out, int64_t *nmh_out);
+/* completeness / contamination / copy-number histogram from per-marker copy numbers, on the device
+ * (ResultsManager.geneCounts + MarkerSet.genomeCheck for an arbitrary {marker: hits} dict, e.g. merger.py:63-88).
+ * marker_count[y] is the copy number of the y-th entry of the sets CSR. */
+int  ckm_genome_check(ckm_engine *e, int32_t nbins, const int64_t *bin_set_off, const int64_t *set_marker_off,
+                      const int32_t *marker_count, int32_t individual_markers, ckm_qa_row *rows_out);
 void ckm_free(void *p);
 
 /* ---- multi-GPU: all-gather of the fixed-width QA rows over NCCL (config #4).  comm is an ncclComm_t
