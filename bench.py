@@ -163,11 +163,11 @@ def run_reference(args):
     t = 0.0
     sumM = 0
     for _ in range(args.steps):
-        dt, sumM, _ = oracle_sample(db_path, bins, cores, n_models=48)
+        dt, sumM, _ = oracle_sample(db_path, bins, cores, n_models=400)
         t += dt
     per_bin = (t / args.steps) * (sumM_all / float(sumM))        # seconds to search one bin against all 5,000 models
     gph = 3600.0 / per_bin
-    sample = "1 bin (%d ORFs) x first 48 of %d models per step, scaled by model positions (%d of %d)" % (ORFS_PER_BIN, N_MODELS, sumM, sumM_all)
+    sample = "1 bin (%d ORFs) x first 400 of %d models per step, scaled by model positions (%d of %d)" % (ORFS_PER_BIN, N_MODELS, sumM, sumM_all)
     line = {"metric": "genomes/hour", "value": gph, "unit": "genomes/hour", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int16/f32",
             "data": "synthetic", "impl": "reference",
@@ -370,16 +370,17 @@ def main():
                          "note": "the stage is DP-cell bound, not HBM bound (SURVEY.md 8d): see gcups"},
             "gcups": {"real_cells_per_step": real_cells, "tile_cells_per_step": cells / args.steps, "ssv_gcups_real": real_cells / ssv_s / 1e9,
                       "ssv_gcups_tile": cells / args.steps / ssv_s / 1e9, "smem_bound_gcups_at_1.9GHz": 148 * 51.2 * 1.9,
-                      "stage_ms_per_step": {"ssv": ssv_ms / args.steps, "msv_exact": msv_ms / args.steps, "bias+vit+fwd+domdef": other_ms / args.steps}},
+                      "stage_ms_per_step": {"ssv": ssv_ms / args.steps, "msv_exact": msv_ms / args.steps, "bias+vit+fwd+domdef": other_ms / args.steps,
+                                            "last_step": {"bias": st.ms_bias, "vit": st.ms_vit, "fwd": st.ms_fwd, "domdef": st.ms_domdef, "total": st.ms_total}}},
             "cascade": {"pairs": int(st.n_pairs), "ssv_cand": int(st.n_ssv_cand), "past_msv": int(st.n_past_msv), "past_bias": int(st.n_past_bias),
                         "past_vit": int(st.n_past_vit), "past_fwd": int(st.n_past_fwd), "rows": int(st.n_reported)},
             "clocks": sampler.summary()}
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        dt, sumM, _ = oracle_sample(db_path, batches[0]['bins'], cores, n_models=48)
+        dt, sumM, _ = oracle_sample(db_path, batches[0]['bins'], cores, n_models=400)
         per_bin = dt * (sumM_all / float(sumM))
         line["cpu_baseline"] = {"value": 3600.0 / per_bin, "unit": "genomes/hour", "cores": cores, "kind": "port",
-                                "sample": "1 bin x first 48 of %d models (%d of %d model positions), %.1f s, scaled" % (nm, sumM, sumM_all, dt)}
+                                "sample": "1 bin x first 400 of %d models (%d of %d model positions), %.1f s, scaled" % (nm, sumM, sumM_all, dt)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

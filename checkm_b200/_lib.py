@@ -56,7 +56,7 @@ class ReduceOpts(C.Structure):
 
 class ReduceMeta(C.Structure):
     _fields_ = [("is_pfam", C.c_void_p), ("is_tigr", C.c_void_p), ("clan", C.c_void_p),
-                ("nest_off", C.c_void_p), ("nest_idx", C.c_void_p), ("has_cut", C.c_void_p), ("cutoffs", C.c_void_p),
+                ("nest_off", C.c_void_p), ("nest_idx", C.c_void_p), ("has_cut", C.c_void_p), ("cutoffs", C.c_void_p), ("row_scores", C.c_void_p),
                 ("scaffold_id", C.c_void_p), ("orf_num", C.c_void_p), ("name_rank", C.c_void_p),
                 ("bin_set_off", C.c_void_p), ("set_marker_off", C.c_void_p), ("set_marker_idx", C.c_void_p)]
 

@@ -31,7 +31,9 @@ struct FwdModel {
 };
 
 // Forward.  rows: 3 shared-memory arrays of >= 32*ceil(M/32)+1 floats.  Returns the Forward score in nats.
-template <bool FULL>
+// EXACT: evaluate the D chain and the E sum strictly in model order (one lane after another), reproducing a scalar
+// left-to-right evaluation bit for bit; used where sampling decisions hang on the matrix (the trace ensemble).
+template <bool FULL, bool EXACT = false>
 __device__ __forceinline__ void forward_rows(const FwdModel &fm, const uint8_t *__restrict__ res, int L, const Specials sp,
                                              float *rowM, float *rowI, float *rowD, int lane,
                                              float *xmx, float *full, int /*unused*/, float *ret_sc) {
@@ -59,22 +61,39 @@ __device__ __forceinline__ void forward_rows(const FwdModel &fm, const uint8_t *
       sv += pd * t0.w;
       sv *= __ldg(rp + k);
       const float nI = oM * t1.y + oI * t1.z;
-      float B = sv * t1.x, T = t1.w;                 // D(k+1) = B + D(k) * T
+      float dk;
+      if (EXACT) {
+        dk = dcarry;                                  // lane 0 holds D(k_first); the others receive theirs in turn
+        for (int l = 0; l < 32; ++l) {
+          const float out = __fadd_rn(__fmul_rn(sv, t1.x), __fmul_rn(dk, t1.w));   // D(k+1) from lane l's M(k), D(k)
+          const float pass = __shfl_sync(0xffffffffu, out, l);
+          if (lane == l + 1) dk = pass;
+          if (l == 31) dcarry = pass;
+          esum = __fadd_rn(esum, __shfl_sync(0xffffffffu, sv, l));                  // running sum of M's in k order (all lanes alike)
+        }
+        if (k > M) dk = 0.0f;
+      } else {
+        float B = sv * t1.x, T = t1.w;                 // D(k+1) = B + D(k) * T
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const float Bl = __shfl_up_sync(0xffffffffu, B, o), Tl = __shfl_up_sync(0xffffffffu, T, o);
-        if (lane >= o) { B = B + Bl * T; T = T * Tl; }
+        for (int o = 1; o < 32; o <<= 1) {
+          const float Bl = __shfl_up_sync(0xffffffffu, B, o), Tl = __shfl_up_sync(0xffffffffu, T, o);
+          if (lane >= o) { B = B + Bl * T; T = T * Tl; }
+        }
+        const float dnext = B + dcarry * T;
+        dk = __shfl_up_sync(0xffffffffu, dnext, 1);
+        if (lane == 0) dk = dcarry;
+        dcarry = __shfl_sync(0xffffffffu, dnext, 31);
+        if (k > M) dk = 0.0f;
+        esum += sv + dk;
       }
-      const float dnext = B + dcarry * T;
-      float dk = __shfl_up_sync(0xffffffffu, dnext, 1);
-      if (lane == 0) dk = dcarry;
-      dcarry = __shfl_sync(0xffffffffu, dnext, 31);
-      if (k > M) dk = 0.0f;
-      esum += sv + dk;
       rowM[k] = sv; rowI[k] = nI; rowD[k] = dk;
       if (FULL) { frow[k] = sv; frow[fm.Mpad + k] = dk; frow[2 * fm.Mpad + k] = nI; }
     }
-    xE = warp_sum_float(esum);
+    if (EXACT) {
+      __syncwarp();
+      for (int k = 1; k <= M; ++k) esum = __fadd_rn(esum, rowD[k]);       // then the D's, again in k order
+      xE = esum;
+    } else xE = warp_sum_float(esum);
     xN = xN * sp.nloop;
     xC = (xC * sp.nloop) + (xE * sp.emove);
     xJ = (xJ * sp.nloop) + (xE * sp.eloop);

@@ -88,11 +88,11 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) ensemble_kernel(EnsembleParams
     float *xf = F + (int64_t)(Lr + 1) * 3 * Mpad;
     float *acc = xf + (int64_t)(Lr + 1) * X_NX, *val = acc + (Lr + 1);
     int *spb = reinterpret_cast<int *>(val + (Lr + 1));       // SPCAP x 5
-    int *label = spb + SPCAP * 5;                            // SPCAP
-    int *epc = label + SPCAP;                                // max(Lr, M) + 2
+    int *label = spb + SPCAP * 5;                            // 3 x SPCAP: available list, stack, cluster assignment
+    int *epc = label + 3 * SPCAP;                            // max(Lr, M) + 2
     int *segbuf = epc + max(Lr, M) + 2;                      // per-trace segments, right-to-left: 64 x 4
     float *n2sc = p.n2sc + pw.row_off;
-    forward_rows<true>(fm, res, Lr, sp, rowM, rowI, rowD, lane, xf, F, 0, nullptr);
+    forward_rows<true, true>(fm, res, Lr, sp, rowM, rowI, rowD, lane, xf, F, 0, nullptr);
     for (int pos = lane; pos <= Lr; pos += 32) acc[pos] = 0.0f;
     __syncwarp();
     Lcg rng; rng.x = mix3(42u, 87654321u, 12345678u); if (rng.x == 0) rng.x = 42;
@@ -136,11 +136,11 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) ensemble_kernel(EnsembleParams
           s1 = (i == 0) ? ST_S : ST_N;
         } else if (s0 == ST_C) {
           pth[0] = (i > 0) ? __fmul_rn(xf[(int64_t)(i - 1) * X_NX + X_C], sp.nloop) : 0.0f;
-          pth[1] = __fmul_rn(xf[(int64_t)i * X_NX + X_E], sp.emove);
+          pth[1] = __fmul_rn(__fmul_rn(xf[(int64_t)i * X_NX + X_E], sp.emove), xf[(int64_t)i * X_NX + X_SCALE]);
           s1 = fchoose(rng, pth, 2) == 0 ? ST_C : ST_E;
         } else if (s0 == ST_J) {
           pth[0] = (i > 0) ? __fmul_rn(xf[(int64_t)(i - 1) * X_NX + X_J], sp.nloop) : 0.0f;
-          pth[1] = __fmul_rn(xf[(int64_t)i * X_NX + X_E], sp.eloop);
+          pth[1] = __fmul_rn(__fmul_rn(xf[(int64_t)i * X_NX + X_E], sp.eloop), xf[(int64_t)i * X_NX + X_SCALE]);
           s1 = fchoose(rng, pth, 2) == 0 ? ST_J : ST_E;
         } else if (s0 == ST_B) {
           pth[0] = __fmul_rn(xf[(int64_t)i * X_NX + X_N], sp.nmove);
@@ -254,49 +254,59 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) ensemble_kernel(EnsembleParams
     }
     nsp = min(nsp, SPCAP);
     for (int pos = reg.i + lane; pos <= reg.j; pos += 32) n2sc[pos] = logf(__fdiv_rn(acc[pos - reg.i + 1], (float)NSAMPLES));
-    // ---- single-linkage clustering = connected components of the link graph (min-label propagation) ----
-    for (int h = lane; h < nsp; h += 32) label[h] = h;
+    // ---- single-linkage clustering, numbering the clusters exactly as the sequential reference does: seed = last
+    // available vertex; pop a vertex, sweep the available list from the top, move every linked vertex to the stack
+    // (filling its hole with the list's last element).  The link tests of a sweep run 32 at a time across the lanes;
+    // the list surgery is replayed identically by every lane. ----
+    int *avail = label, *stack = label + SPCAP, *assign = label + 2 * SPCAP;
+    for (int h = lane; h < nsp; h += 32) avail[h] = h;
     __syncwarp();
-    for (int iter = 0; iter < 64; ++iter) {
-      int changed = 0;
-      const long npair = (long)nsp * (nsp - 1) / 2;
-      for (int a = 0; a < nsp; ++a) {
-        for (int b = a + 1 + lane; b < nsp; b += 32) {
-          const int la = label[a], lb = label[b];
-          if (la != lb && sp_link(spb + a * 5, spb + b * 5)) {
-            const int mn = min(la, lb);
-            atomicMin(&label[a], mn); atomicMin(&label[b], mn);
-            changed = 1;
+    int na = nsp, nb = 0, nc = 0;
+    while (na > 0) {
+      int v = avail[na - 1]; na--;
+      stack[nb++] = v;
+      while (nb > 0) {
+        v = stack[--nb];
+        assign[v] = nc;
+        for (int base = na - 1; base >= 0; base -= 32) {
+          const int pos = base - lane;
+          bool linked = false;
+          if (pos >= 0) linked = sp_link(spb + v * 5, spb + avail[pos] * 5);
+          unsigned mask = __ballot_sync(0xffffffffu, linked);
+          while (mask != 0u) {
+            const int l = __ffs(mask) - 1;          // lowest lane = highest position first, as the downward sweep does
+            mask &= mask - 1;
+            const int pz = base - l;
+            const int w = avail[pz];
+            avail[pz] = avail[na - 1];
+            na--;
+            stack[nb++] = w;
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
-      (void)npair;
-      // pointer jumping
-      for (int h = lane; h < nsp; h += 32) { int l = label[h]; while (label[l] != l) l = label[l]; label[h] = l; }
-      __syncwarp();
-      if (!__any_sync(0xffffffffu, changed)) break;
+      nc++;
     }
+    __syncwarp();
     // ---- significant clusters -> envelopes (lane 0; the lists are short) ----
     if (lane == 0) {
       int nout = 0;
       Envelope *eo = ep.env_out + (int64_t)ri * MAXENV;
-      for (int c = 0; c < nsp; ++c) {
-        if (label[c] != c) continue;
+      for (int c = 0; c < nc; ++c) {
         int idx_of_last = -1, ninc = 0;
-        for (int h = 0; h < nsp; ++h) if (label[h] == c) { if (spb[h * 5] != idx_of_last) ninc++; idx_of_last = spb[h * 5]; }
+        for (int h = 0; h < nsp; ++h) if (assign[h] == c) { if (spb[h * 5] != idx_of_last) ninc++; idx_of_last = spb[h * 5]; }
         if ((float)ninc / (float)NSAMPLES < 0.25f) continue;
         int imin = 1 << 30, jmin = 1 << 30, imax = 0, jmax = 0;
-        for (int h = 0; h < nsp; ++h) if (label[h] == c) {
+        for (int h = 0; h < nsp; ++h) if (assign[h] == c) {
           imin = min(imin, spb[h * 5 + 1]); imax = max(imax, spb[h * 5 + 1]);
           jmin = min(jmin, spb[h * 5 + 2]); jmax = max(jmax, spb[h * 5 + 2]);
         }
         int cmv, best_i, best_j;
         for (int z = 0; z <= imax - imin; ++z) epc[z] = 0;
-        for (int h = 0; h < nsp; ++h) if (label[h] == c) epc[spb[h * 5 + 1] - imin]++;
+        for (int h = 0; h < nsp; ++h) if (assign[h] == c) epc[spb[h * 5 + 1] - imin]++;
         for (cmv = 0, best_i = imin; best_i <= imax; ++best_i) { cmv += epc[best_i - imin]; if ((float)cmv / (float)ninc >= 0.02f) break; }
         for (int z = 0; z <= jmax - jmin; ++z) epc[z] = 0;
-        for (int h = 0; h < nsp; ++h) if (label[h] == c) epc[spb[h * 5 + 2] - jmin]++;
+        for (int h = 0; h < nsp; ++h) if (assign[h] == c) epc[spb[h * 5 + 2] - jmin]++;
         for (cmv = 0, best_j = jmax; best_j >= jmin; --best_j) { cmv += epc[best_j - jmin]; if ((float)cmv / (float)ninc >= 0.02f) break; }
         if (best_i > best_j) continue;
         if (nout < MAXENV) { eo[nout].pair = reg.pair; eo[nout].i = best_i; eo[nout].j = best_j; eo[nout].null2_done = 1; eo[nout].scratch_off = 0; nout++; }
@@ -320,7 +330,7 @@ int run_ensembles(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, Domde
     const Region &r = regs[multi_idx[i]];
     const int64_t Lr = r.j - r.i + 1, M = m->models[pairs[r.pair].model].M, Mpad = ((M + 1) + 31) / 32 * 32 + 32;
     off[i] = tot;
-    tot += (Lr + 1) * 3 * Mpad + (Lr + 1) * X_NX + 2 * (Lr + 1) + (int64_t)SPCAP * 6 + std::max(Lr, M) + 2 + 256 + 64;
+    tot += (Lr + 1) * 3 * Mpad + (Lr + 1) * X_NX + 2 * (Lr + 1) + (int64_t)SPCAP * 8 + std::max(Lr, M) + 2 + 256 + 64;
     tot = (tot + 63) / 64 * 64;
   }
   void *d_regs = nullptr, *d_idx = nullptr, *d_off = nullptr, *d_scr = nullptr, *d_env = nullptr, *d_cnt = nullptr;

@@ -30,6 +30,7 @@ struct RModel {
 
 struct RParams {
   const ckm_hit *hits; int64_t nhits;
+  const double *row_scores;
   RRow *rows;
   const RModel *models;
   const int64_t *nest_off; const int32_t *nest_idx;
@@ -72,8 +73,11 @@ __global__ void r0_round_rows(RParams p) {
     RRow r;
     r.bin = h.bin; r.seq = h.seq; r.model = h.model; r.tlen = h.tlen; r.qlen = h.qlen;
     r.hmm_from = h.hmm_from; r.hmm_to = h.hmm_to; r.ali_from = h.ali_from; r.ali_to = h.ali_to; r.env_from = h.env_from; r.env_to = h.env_to;
-    r.full_score = rint((double)h.full_score * 10.0) / 10.0;
-    r.dom_score = rint((double)h.dom_score * 10.0) / 10.0;
+    if (p.row_scores != nullptr) { r.full_score = p.row_scores[2 * i]; r.dom_score = p.row_scores[2 * i + 1]; }
+    else {
+      r.full_score = rint((double)h.full_score * 10.0) / 10.0;
+      r.dom_score = rint((double)h.dom_score * 10.0) / 10.0;
+    }
     round_evalue(h.full_evalue, r.e_exp, r.e_mant);
     round_evalue(h.i_evalue, r.i_exp, r.i_mant);
     p.rows[i] = r;
@@ -402,6 +406,7 @@ extern "C" int ckm_reduce(ckm_engine *e, int32_t nmodels_in, int32_t nseq_in, in
   p.nhits = nhits; p.nseg = nseg; p.nbins = nbins; p.nmodels = nmodels; p.opts = *opts;
   const size_t nh = (size_t)std::max<int64_t>(nhits, 1);
   ckm_hit *d_hits; UP(d_hits, hits, sizeof(ckm_hit) * (size_t)nhits); p.hits = d_hits;
+  if (meta->row_scores != nullptr && nhits > 0) { double *d_rs; UP(d_rs, meta->row_scores, sizeof(double) * 2 * (size_t)nhits); p.row_scores = d_rs; }
   p.rows = (RRow *)dalloc(sizeof(RRow) * nh); p.list = (int32_t *)dalloc(sizeof(int32_t) * nh); p.list_len = (int32_t *)dalloc(sizeof(int32_t) * std::max(nseg, 1));
   p.filtered = (uint8_t *)dalloc(nh); p.first_app = (int64_t *)dalloc(sizeof(int64_t) * nh);
   p.mh = (ckm_marker_hit *)dalloc(sizeof(ckm_marker_hit) * nh); p.mh_len = (int32_t *)dalloc(sizeof(int32_t) * std::max(nseg, 1));

@@ -85,6 +85,7 @@ def _decimal_split(x):
 def _parse_table_text(path):
     """domtblout text -> (rows, names, descs, query (name, acc) per model id) in file order."""
     rows = []
+    parsed = []
     names, name_idx, descs = [], {}, []
     qids, qid_idx = [], {}
     with open(path) as f:
@@ -102,18 +103,19 @@ def _parse_table_text(path):
             if q is None:
                 q = qid_idx[(hit.query_name, hit.query_accession)] = len(qids)
                 qids.append((hit.query_name, hit.query_accession))
+            parsed.append(hit)
             rows.append((0, s, q, hit.target_length, hit.query_length, hit.dom, hit.ndom, hit.hmm_from, hit.hmm_to,
                          hit.ali_from, hit.ali_to, hit.env_from, hit.env_to, hit.full_score, hit.full_bias, hit.dom_score,
                          hit.dom_bias, hit.acc, hit.full_e_value, hit.c_evalue, hit.i_evalue, 0.0, 0.0))
     arr = np.array(rows, dtype=HIT_DTYPE) if rows else np.zeros(0, dtype=HIT_DTYPE)
-    return arr, names, descs, qids
+    return arr, names, descs, qids, parsed
 
 
 def load_hit_table(path):
     """Rows of one bin's domtblout: binary side-car if present and not older than the text, else the text."""
     side = path + '.ckm.npz'
     if os.path.exists(side) and os.path.exists(path) and os.path.getmtime(side) >= os.path.getmtime(path):
-        return read_sidecar(path)
+        return read_sidecar(path) + (None,)
     return _parse_table_text(path)
 
 
@@ -170,7 +172,7 @@ class ResultsParser(object):
                 tables[binId] = load_hit_table(path)
             except IOError as detail:
                 sys.stderr.write(str(detail) + "\n")          # the reference carries on with an empty result
-                tables[binId] = (np.zeros(0, dtype=HIT_DTYPE), [], [], [])
+                tables[binId] = (np.zeros(0, dtype=HIT_DTYPE), [], [], [], None)
         try:
             reduced = self._reduce(binIds, tables, bIgnoreThresholds, evalueThreshold, lengthThreshold,
                                    bSkipPseudoGeneCorrection, bSkipAdjCorrection)
@@ -232,9 +234,17 @@ class ResultsParser(object):
         seq_base, bases = 0, {}
         scaf_ids = {}
         row_q = {}
+        text_scores, any_text, parsed_all = [], False, []
         for b, binId in enumerate(binIds):
-            rows, names, descs, qids = tables[binId]
+            rows, names, descs, qids, parsed = tables[binId]
             bases[binId] = seq_base
+            if parsed is not None:
+                any_text = True
+                text_scores.extend((h.full_score, h.dom_score) for h in parsed)
+                parsed_all.extend(parsed)
+            else:
+                text_scores.extend((float('%6.1f' % r['full_score']), float('%6.1f' % r['dom_score'])) for r in rows)
+                parsed_all.extend([None] * len(rows))
             order = {n: r for r, n in enumerate(sorted(set(names)))}
             for n in names:
                 cut_at = n.rfind('_')
@@ -286,6 +296,8 @@ class ResultsParser(object):
         meta.name_rank = name_rank.ctypes.data if nseq else None
         meta.has_cut = has.ctypes.data
         meta.cutoffs = cut.ctypes.data
+        row_scores = np.asarray(text_scores, dtype=np.float64).reshape(-1, 2) if (any_text and len(hits)) else None
+        meta.row_scores = row_scores.ctypes.data if row_scores is not None else None
         qa = C.POINTER(_lib.QaRow)()
         nqa = C.c_int32()
         mh = C.POINTER(_lib.MarkerHit)()
@@ -307,7 +319,7 @@ class ResultsParser(object):
         for rec in marker_hits:
             per_bin[int(rec['bin'])].append(rec)
         for b, binId in enumerate(binIds):
-            rows, names, descs, qids = tables[binId]
+            rows, names, descs, qids, _parsed = tables[binId]
             base = bases[binId]
             groups, keys = {}, {}
             for pos, rec in enumerate(per_bin.get(b, [])):
@@ -323,12 +335,18 @@ class ResultsParser(object):
                     if (qa_ if qa_ not in ('-', '') else qn) == acc:
                         qname = qn
                         break
-                hit = _hit_from_row(src, names[a], descs[a] if descs else '', qname if qname is not None else acc, acc)
+                original = parsed_all[int(rec['src_row'])]
+                if original is not None:
+                    hit = MarkerHit()
+                    for f in MarkerHit.__slots__:
+                        setattr(hit, f, getattr(original, f))
+                else:
+                    hit = _hit_from_row(src, names[int(src['seq']) - base], descs[int(src['seq']) - base] if descs else '',
+                                        qname if qname is not None else acc, acc)
                 if rec['seq_b'] >= 0:
                     bname = names[int(rec['seq_b']) - base]
+                    # the merged object is hits[i] mutated (resultsParser.py:451-470): scores and description stay
                     hit.target_name = DefaultValues.SEQ_CONCAT_CHAR.join([names[a], bname])
-                    # the merged object is hits[i] mutated (resultsParser.py:451-470): its scores and description stay
-                    hit.target_description = descs[int(src['seq']) - base] if descs else ''
                 hit.target_length = int(rec['target_length'])
                 hit.hmm_from, hit.hmm_to = int(rec['hmm_from']), int(rec['hmm_to'])
                 hit.ali_from, hit.ali_to = int(rec['ali_from']), int(rec['ali_to'])

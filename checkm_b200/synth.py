@@ -200,6 +200,14 @@ def perturbed_model_lengths(rng, n, lo=30, hi=1500, mean=240):
     return np.clip(x, lo, hi).astype(np.int64)
 
 
+def fitted_stats(M):
+    """(MSV mu, Viterbi mu, Forward tau, lambda) as a function of model length, least-squares fitted to the 43 real,
+    HMMER-calibrated CPR models (residual s.d. 0.17 / 0.16 / 0.24 bits) -- keeps the filter pass rates of synthetic
+    models near their nominal 2% / 0.1% / 1e-5."""
+    x = np.log2(max(M, 2))
+    return (-2.599826 - 1.03052763 * x, -2.57804831 - 1.13368047 * x, 1.65869172 - 0.86205053 * x, 0.69315 + 1.8 / max(M, 2))
+
+
 def _nl(p):
     return '      *' if p <= 0.0 else '%9.5f' % (-np.log(p))[:9].strip().rjust(9) if False else ('%.5f' % (-np.log(p)))
 
@@ -209,7 +217,7 @@ def write_hmms(path, models, stats=None):
     with open(path, 'w') as f:
         for i, h in enumerate(models):
             M = h.M
-            mu = stats[i] if stats is not None else (-8.0 - 0.9 * np.log2(max(M, 2) / 50.0), -8.6 - 0.9 * np.log2(max(M, 2) / 50.0), -4.0, 0.71)
+            mu = stats[i] if stats is not None else fitted_stats(M)
             f.write('HMMER3/f [3.1b2 | February 2015]\n')
             f.write('NAME  %s\n' % h.name)
             if h.acc and h.acc != h.name:
@@ -314,8 +322,8 @@ def make_model_db_fast(path, src_path, lengths, seed=0, prefix='SYN'):
             f.write('HMMER3/f [3.1b2 | February 2015]\nNAME  %s%05d\n' % (prefix, n))
             f.write('ACC   %s\n' % ('PF%05d.1' % (90000 + n) if n % 2 == 0 else 'TIGR%05d' % (90000 + n)))
             f.write('LENG  %d\nALPH  amino\nRF    no\nMM    no\nCONS  no\nCS    no\nMAP   no\nNSEQ  10\nEFFN  1.000000\nCKSUM 0\n' % M)
-            mu = -8.0 - 0.9 * np.log2(max(M, 2) / 50.0)
-            f.write('STATS LOCAL MSV      %8.4f  0.71000\nSTATS LOCAL VITERBI  %8.4f  0.71000\nSTATS LOCAL FORWARD   -4.0000  0.71000\n' % (mu, mu - 0.6))
+            st = fitted_stats(M)
+            f.write('STATS LOCAL MSV      %8.4f  %.5f\nSTATS LOCAL VITERBI  %8.4f  %.5f\nSTATS LOCAL FORWARD  %8.4f  %.5f\n' % (st[0], st[3], st[1], st[3], st[2], st[3]))
             f.write(first['hdr2'][0] + '\n' + first['hdr2'][1] + '\n')
             if first['compo'] is not None:
                 f.write(first['compo'] + '\n')

@@ -190,6 +190,8 @@ typedef struct {
   const int64_t *nest_off; const int32_t *nest_idx;
   const int32_t *has_cut;                        /* nmodels x {ga, tc, nc}: cutoff present                          */
   const double  *cutoffs;                        /* nmodels x {ga0, ga1, tc0, tc1, nc0, nc1} as float() reads them  */
+  const double  *row_scores;                     /* optional, nhits x {full_score, dom_score}: the values exactly as the
+                                                    domtblout text gave them (text path); NULL = round the binary scores to %.1f */
   const int32_t *scaffold_id, *orf_num;          /* per sequence */
   const int32_t *name_rank;                      /* per sequence: rank of the name in string order (for "A&&B") */
   const int64_t *bin_set_off;                    /* optional: nbins+1; sets of bin b are [bin_set_off[b], bin_set_off[b+1]) */

@@ -1042,11 +1042,11 @@ static int stochastic_trace(lcg_t *rng, const orc_profile *p, specials sp, const
     case ST_N: s1 = (i == 0) ? ST_S : ST_N; break;
     case ST_C:
       path[0] = (i > 0) ? ox->xmx[(i - 1) * X_NX + X_C] * sp.nloop : 0.0f;
-      path[1] = ox->xmx[i * X_NX + X_E] * sp.emove;
+      path[1] = ox->xmx[i * X_NX + X_E] * sp.emove * ox->xmx[i * X_NX + X_SCALE];   /* row i may have been rescaled */
       s1 = fchoose(rng, path, 2) == 0 ? ST_C : ST_E; break;
     case ST_J:
       path[0] = (i > 0) ? ox->xmx[(i - 1) * X_NX + X_J] * sp.nloop : 0.0f;
-      path[1] = ox->xmx[i * X_NX + X_E] * sp.eloop;
+      path[1] = ox->xmx[i * X_NX + X_E] * sp.eloop * ox->xmx[i * X_NX + X_SCALE];
       s1 = fchoose(rng, path, 2) == 0 ? ST_J : ST_E; break;
     case ST_B:
       path[0] = ox->xmx[i * X_NX + X_N] * sp.nmove;
