@@ -36,5 +36,5 @@ def gather_rows(rows, dist, device=None):
         mine[:len(rows) * width] = torch.from_numpy(np.ascontiguousarray(rows).view(np.uint8).reshape(-1).copy()).to(dev)
     out = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(out, mine)
-    parts = [np.frombuffer(o.cpu().numpy().tobytes()[:c * width], dtype=rows.dtype) for o, c in zip(out, counts)]
-    return np.concatenate(parts) if parts else rows
+    blob = b''.join(o.cpu().numpy().tobytes()[:c * width] for o, c in zip(out, counts))      # byte-wise: keeps struct padding intact
+    return np.frombuffer(blob, dtype=rows.dtype).copy()
