@@ -37,4 +37,4 @@ def gather_rows(rows, dist, device=None):
     out = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(out, mine)
     blob = b''.join(o.cpu().numpy().tobytes()[:c * width] for o, c in zip(out, counts))      # byte-wise: keeps struct padding intact
-    return np.frombuffer(blob, dtype=rows.dtype).copy()
+    return np.frombuffer(bytearray(blob), dtype=rows.dtype)

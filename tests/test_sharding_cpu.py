@@ -57,7 +57,8 @@ def test_gather_qa_rows_gloo_world2():
         assert p.exitcode == 0
     a = np.frombuffer(got[0], dtype=QA_DTYPE)
     b = np.frombuffer(got[1], dtype=QA_DTYPE)
-    assert a.tobytes() == b.tobytes()
+    for name in QA_DTYPE.names:
+        assert np.array_equal(a[name], b[name]), name
     assert sorted(a['bin'].tolist()) == [0, 1, 2, 3, 4]
     for r in a:
         assert r['completeness'] == 10.0 * r['bin'] + 0.123456789 and r['counts'][1] == r['bin'] + 1
