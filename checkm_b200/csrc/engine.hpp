@@ -52,8 +52,9 @@ struct ModelScalars {
   int16_t base_w, xw_e_loop, xw_e_move, pad16;
   float   scale_b, scale_w;
   float   evparam[6];
-  float   msv_A;         // model part of the SSV candidate threshold (see kernels_msv.cu)
-  float   pad;
+  int32_t ddbound_w;     // lazy-F bound of the Viterbi filter
+  int32_t vq;            // lane-blocked class: cells per lane (2,4,8,16), 0 = model too long for the blocked kernels
+  int64_t blk_off;       // offset of the model's lane-blocked tables (in units of 32 lanes x vq cells)
 };
 
 struct Candidate {       // an (ORF, HMM) pair moving down the cascade
@@ -79,6 +80,11 @@ struct ckm_models {
   float    *d_rfv = nullptr;      // per model [KPAD][Mpad]
   float    *d_tfv = nullptr;      // per model [Mpad][8]
   float    *d_bias_eo = nullptr;  // per model [KPAD][2]
+  // lane-blocked copies for the register-resident survivor kernels: lane l owns positions k = l*vq + q + 1
+  uint4    *d_twb = nullptr;      // per model [vq][32] : 8 int16 transitions of cell (q, lane)
+  uint32_t *d_rwb = nullptr;      // per model [KPAD][vq/2][32] : two int16 emissions (q = 2j, 2j+1)
+  float4   *d_tfb = nullptr;      // per model [vq][32][2] : 8 fp32 transitions
+  float    *d_rfb = nullptr;      // per model [KPAD][vq][32] : fp32 emission odds
   int64_t   total_cols = 0;
   int       maxM = 0;
   // SSV tiles

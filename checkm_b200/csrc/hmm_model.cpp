@@ -241,6 +241,14 @@ void configure_profile(Model &m) {
     }
     m.xw_e_loop = wordify(m.scale_w, (float)-kLog2);
     m.xw_e_move = wordify(m.scale_w, (float)-kLog2);
+    // lazy-F bound: the best a D->D->M detour can do relative to entering the same match state from B
+    m.ddbound_w = -32768;
+    for (int k = 2; k < M - 1; ++k) {
+      int dd = (int)wordify(m.scale_w, m.tsc[(size_t)k * H_N + H_DD]);
+      dd += (int)wordify(m.scale_w, m.tsc[(size_t)(k + 1) * H_N + H_DM]);
+      dd -= (int)wordify(m.scale_w, m.bm[k + 2]);
+      if (dd > m.ddbound_w) m.ddbound_w = dd;
+    }
   }
 
   // ---- Forward/Backward odds ----

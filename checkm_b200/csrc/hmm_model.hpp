@@ -44,6 +44,7 @@ struct Model {
   std::vector<int16_t> rwv;            // KP*(M+1)
   std::vector<int16_t> twv;            // (M+1)*8
   int16_t base_w = 12000, xw_e_loop = 0, xw_e_move = 0;
+  int32_t ddbound_w = -32768;
   float   scale_w = 0;
   // Forward / Backward
   std::vector<float>   rfv;            // KP*(M+1) match odds ratios

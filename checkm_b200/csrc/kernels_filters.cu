@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) vit_kernel(FilterParams p) {
     Candidate cd = p.in[c];
     const int s = cd.seq, m = cd.model, L = p.len[s];
     const ModelScalars ms = p.ms[m];
+    if (ms.vq != 0) continue;               // handled by vit2_kernel<Q>
     bool pass = true;
     if (cd.P > p.F2) {
       const int M = ms.M, nchunk = (M + 31) >> 5;
@@ -157,6 +158,126 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) vit_kernel(FilterParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// ViterbiFilter, lane-blocked: lane l keeps model positions l*Q+1 .. l*Q+Q of the current row in registers (M, I, D
+// and the 8 transitions of each position), so a row costs two boundary shuffles, two warp reductions and -- only when
+// the lazy-F test says a D->D path could matter -- one max-plus scan across the lanes.  Same int16 semantics as above.
+// ------------------------------------------------------------------------------------------------
+template <int Q>
+__global__ void __launch_bounds__(128) vit2_kernel(FilterParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int n = min(*p.in_count, p.in_cap);
+  for (int c = blockIdx.x * wpb + warp; c < n; c += gridDim.x * wpb) {
+    Candidate cd = p.in[c];
+    const int m = cd.model;
+    const ModelScalars ms = p.ms[m];
+    if (ms.vq != Q) continue;
+    const int s = cd.seq, L = p.len[s];
+    bool pass = true;
+    if (cd.P > p.F2) {
+      // transitions of my Q positions, unpacked once: {BM, MM, IM, DM, MD, MI, II, DD}
+      int tr[Q][8];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const uint4 t = __ldg(p.twb + (ms.blk_off + q) * 32 + lane);
+        tr[q][0] = (int16_t)(t.x & 0xffff); tr[q][1] = (int16_t)(t.x >> 16); tr[q][2] = (int16_t)(t.y & 0xffff); tr[q][3] = (int16_t)(t.y >> 16);
+        tr[q][4] = (int16_t)(t.z & 0xffff); tr[q][5] = (int16_t)(t.z >> 16); tr[q][6] = (int16_t)(t.w & 0xffff); tr[q][7] = (int16_t)(t.w >> 16);
+      }
+      const uint32_t *rwb = p.rwb + ms.blk_off * 32 * (KPAD / 2) + lane;
+      int Mx[Q], Ix[Q], Dx[Q];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) { Mx[q] = -32768; Ix[q] = -32768; Dx[q] = -32768; }
+      const int tmove = p.tmove_w[s], ddbound = ms.ddbound_w;
+      int xN = ms.base_w, xB = xN + tmove, xJ = -32768, xC = -32768;
+      bool overflow = false;
+      const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + p.off[s]);
+      const int nblk = (L + 15) >> 4;
+      for (int b = 0; b < nblk && !overflow; ++b) {
+        const uint4 r16 = __ldg(rp + b);
+        const uint32_t w4[4] = {r16.x, r16.y, r16.z, r16.w};
+        const int rows = min(16, L - b * 16);
+        for (int r = 0; r < rows; ++r) {
+          const uint32_t x = (w4[r >> 2] >> (8 * (r & 3))) & 0xffu;
+          uint32_t e2[Q / 2];
+#pragma unroll
+          for (int j = 0; j < Q / 2; ++j) e2[j] = __ldg(rwb + (x * (Q / 2) + j) * 32);
+          // row i-1 values of the position just below my block
+          const uint32_t packed = ((uint32_t)(uint16_t)Mx[Q - 1]) | ((uint32_t)(uint16_t)Ix[Q - 1] << 16);
+          uint32_t bmi = __shfl_up_sync(0xffffffffu, packed, 1);
+          int bd = __shfl_up_sync(0xffffffffu, Dx[Q - 1], 1);
+          if (lane == 0) { bmi = 0x80008000u; bd = -32768; }
+          const int pm_in = (int16_t)(bmi & 0xffff), pi_in = (int16_t)(bmi >> 16);
+          int xEl = -32768, dml = -32768;
+          int md[Q];
+#pragma unroll
+          for (int q = Q - 1; q >= 0; --q) {
+            const int pm = (q > 0) ? Mx[q - 1] : pm_in, pi = (q > 0) ? Ix[q - 1] : pi_in, pd = (q > 0) ? Dx[q - 1] : bd;
+            int sv = __viaddmax_s32(xB, tr[q][0], -32768);
+            sv = __viaddmax_s32(pm, tr[q][1], sv);
+            sv = __viaddmax_s32(pi, tr[q][2], sv);
+            sv = __viaddmax_s32(pd, tr[q][3], sv);
+            const int e = (q & 1) ? ((int)e2[q >> 1] >> 16) : (int)(int16_t)(e2[q >> 1] & 0xffffu);
+            sv = min(__viaddmax_s32(sv, e, -32768), 32767);
+            const int nI = __viaddmax_s32(Ix[q], tr[q][6], __viaddmax_s32(Mx[q], tr[q][5], -32768));
+            md[q] = __viaddmax_s32(sv, tr[q][4], -32768);
+            xEl = max(xEl, sv); dml = max(dml, md[q]);
+            Mx[q] = sv; Ix[q] = nI;
+          }
+          const int xE = __reduce_max_sync(0xffffffffu, xEl);
+          if (xE >= 32767) { overflow = true; break; }
+          xC = max(xC, xE + (int)ms.xw_e_move);
+          xJ = max(xJ, xE + (int)ms.xw_e_loop);
+          xB = max(xJ + tmove, xN + tmove);
+          xC = max(xC, -32768); xJ = max(xJ, -32768); xB = max(xB, -32768);
+          const int Dmax = __reduce_max_sync(0xffffffffu, dml);
+          if (Dmax + ddbound > xB) {
+            // full D->D: composite of my block f(d) = max(Bb, d + Tb), exclusive max-plus scan across lanes
+            int Bb = -32768, Tb = 0;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) { Bb = max(md[q], Bb + tr[q][7]); Bb = max(Bb, -32768); Tb = max(Tb + tr[q][7], -(1 << 24)); }
+            int Bs = Bb, Ts = Tb;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int Bl = __shfl_up_sync(0xffffffffu, Bs, o), Tl = __shfl_up_sync(0xffffffffu, Ts, o);
+              if (lane >= o) { Bs = max(Bs, Bl + Ts); Ts = max(Ts + Tl, -(1 << 24)); }
+            }
+            int din = __shfl_up_sync(0xffffffffu, max(Bs, -32768), 1);      // D(i, first k of my block)
+            if (lane == 0) din = -32768;
+            int d = din;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) { Dx[q] = d; d = max(max(md[q], d + tr[q][7]), -32768); }
+          } else {
+            // lazy F: no D->D path can beat entering from B; keep the M->D partials only
+            int din = __shfl_up_sync(0xffffffffu, md[Q - 1], 1);
+            if (lane == 0) din = -32768;
+#pragma unroll
+            for (int q = Q - 1; q >= 1; --q) Dx[q] = md[q - 1];
+            Dx[0] = din;
+          }
+        }
+      }
+      float vsc;
+      if (overflow) vsc = INFINITY;
+      else if (xC > -32768) {
+        vsc = __fsub_rn(__fadd_rn((float)xC, (float)tmove), (float)ms.base_w);
+        vsc = __fdiv_rn(vsc, ms.scale_w);
+        vsc = __fsub_rn(vsc, 3.0f);
+      } else vsc = -INFINITY;
+      cd.vitsc = vsc;
+      const float seq_score = __fdiv_rn(__fsub_rn(vsc, cd.filtersc), 0.69314718055994529f);
+      const double P = gumbel_surv((double)seq_score, (double)ms.evparam[2], (double)ms.evparam[3]);
+      cd.P = P;
+      pass = (P <= p.F2);
+      if (lane == 0 && p.dense_vit != nullptr) p.dense_vit[(int64_t)p.model_slot[m] * p.nseq + s] = vsc;
+    }
+    if (lane == 0 && pass) {
+      const int pos = atomicAdd(p.out_count, 1);
+      if (pos < p.out_cap) p.out[pos] = cd;
+      if (p.dense_passed != nullptr) atomicOr_u8(p.dense_passed, (int64_t)p.model_slot[m] * p.nseq + s, 4);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Forward row engine (shared by the parser here and by the domain-definition stage)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FWD_WARPS * 32) fwd_kernel(FilterParams p) {
@@ -197,6 +318,14 @@ int launch_bias(const FilterParams &p, int grid, cudaStream_t st) {
   bias_kernel<<<grid, 128, 0, st>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? CKM_OK : cuda_fail(e, "bias_kernel launch");
+}
+int launch_vit2(const FilterParams &p, int grid, cudaStream_t st) {
+  vit2_kernel<2><<<grid, 128, 0, st>>>(p);
+  vit2_kernel<4><<<grid, 128, 0, st>>>(p);
+  vit2_kernel<8><<<grid, 128, 0, st>>>(p);
+  vit2_kernel<16><<<grid, 128, 0, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? CKM_OK : cuda_fail(e, "vit2_kernel launch");
 }
 int launch_vit(const FilterParams &p, int grid, cudaStream_t st) {
   const size_t smem = (size_t)VIT_WARPS * 3 * p.row_elems * sizeof(int16_t);

@@ -150,7 +150,7 @@ static void build_tiles(ckm_models &db, std::vector<uint8_t> &blob) {
 int models_build_device(ckm_models &db) {
   const int n = (int)db.models.size();
   std::vector<ModelScalars> sc(n);
-  int64_t cols = 0;
+  int64_t cols = 0, blk_units = 0;
   db.maxM = 0;
   for (int i = 0; i < n; ++i) {
     const Model &m = db.models[i];
@@ -162,6 +162,10 @@ int models_build_device(ckm_models &db) {
     s.base_w = m.base_w; s.xw_e_loop = m.xw_e_loop; s.xw_e_move = m.xw_e_move;
     s.scale_b = m.scale_b; s.scale_w = m.scale_w;
     for (int z = 0; z < 6; ++z) s.evparam[z] = m.evparam[z];
+    s.ddbound_w = m.ddbound_w;
+    s.vq = (m.M <= 64) ? 2 : (m.M <= 128) ? 4 : (m.M <= 256) ? 8 : (m.M <= 512) ? 16 : 0;
+    s.blk_off = blk_units;
+    blk_units += s.vq;
     db.maxM = std::max(db.maxM, m.M);
   }
   if (cols > (int64_t)1 << 30) { set_error("model database too large"); return CKM_ENOMEM; }
@@ -185,7 +189,43 @@ int models_build_device(ckm_models &db) {
       }
     for (int x = 0; x < KP; ++x) { beo[((size_t)i * KPAD + x) * 2] = m.bias_eo[x][0]; beo[((size_t)i * KPAD + x) * 2 + 1] = m.bias_eo[x][1]; }
   }
+  // lane-blocked tables
+  std::vector<uint4> twb((size_t)std::max<int64_t>(blk_units, 1) * 32);
+  std::vector<uint32_t> rwb((size_t)std::max<int64_t>(blk_units, 1) * 32 * KPAD / 2 + 32);
+  std::vector<float4> tfb((size_t)std::max<int64_t>(blk_units, 1) * 32 * 2);
+  std::vector<float> rfb((size_t)std::max<int64_t>(blk_units, 1) * 32 * KPAD);
+  for (int i = 0; i < n; ++i) {
+    const Model &m = db.models[i];
+    const ModelScalars &s = sc[i];
+    const int Q = s.vq;
+    if (Q == 0) continue;
+    const size_t W1 = (size_t)m.M + 1;
+    for (int q = 0; q < Q; ++q)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int k = lane * Q + q + 1;
+        int16_t tw[8]; float tf[8];
+        for (int z = 0; z < 8; ++z) { tw[z] = (k <= m.M) ? m.twv[(size_t)k * T_N + z] : (int16_t)-32768; tf[z] = (k <= m.M) ? m.tfv[(size_t)k * T_N + z] : 0.0f; }
+        uint4 u;
+        u.x = (uint16_t)tw[0] | ((uint32_t)(uint16_t)tw[1] << 16); u.y = (uint16_t)tw[2] | ((uint32_t)(uint16_t)tw[3] << 16);
+        u.z = (uint16_t)tw[4] | ((uint32_t)(uint16_t)tw[5] << 16); u.w = (uint16_t)tw[6] | ((uint32_t)(uint16_t)tw[7] << 16);
+        twb[((size_t)s.blk_off + q) * 32 + lane] = u;
+        tfb[(((size_t)s.blk_off + q) * 32 + lane) * 2] = make_float4(tf[0], tf[1], tf[2], tf[3]);
+        tfb[(((size_t)s.blk_off + q) * 32 + lane) * 2 + 1] = make_float4(tf[4], tf[5], tf[6], tf[7]);
+        for (int x = 0; x < KPAD; ++x) {
+          const int16_t ew = (k <= m.M && x < KP) ? m.rwv[(size_t)x * W1 + k] : (int16_t)-32768;
+          const float ef = (k <= m.M && x < KP) ? m.rfv[(size_t)x * W1 + k] : 0.0f;
+          // emissions of a model: [x][Q/2][32] words at (blk_off*32*KPAD/2) ; floats [x][Q][32] at blk_off*32*KPAD
+          uint32_t &w = rwb[(size_t)s.blk_off * 32 * KPAD / 2 + ((size_t)x * (Q / 2) + (q >> 1)) * 32 + lane];
+          if (q & 1) w = (w & 0x0000ffffu) | ((uint32_t)(uint16_t)ew << 16); else w = (w & 0xffff0000u) | (uint16_t)ew;
+          rfb[(size_t)s.blk_off * 32 * KPAD + ((size_t)x * Q + q) * 32 + lane] = ef;
+        }
+      }
+  }
   int st;
+  if ((st = upload(&db.d_twb, twb))) return st;
+  if ((st = upload(&db.d_rwb, rwb))) return st;
+  if ((st = upload(&db.d_tfb, tfb))) return st;
+  if ((st = upload(&db.d_rfb, rfb))) return st;
   if ((st = upload(&db.d_scalars, sc))) return st;
   if ((st = upload(&db.d_rbv, rbv))) return st;
   if ((st = upload(&db.d_rwv, rwv))) return st;
@@ -207,7 +247,7 @@ int models_build_device(ckm_models &db) {
 
 void models_free_device(ckm_models &db) {
   cudaFree(db.d_scalars); cudaFree(db.d_rbv); cudaFree(db.d_rwv); cudaFree(db.d_twv); cudaFree(db.d_rfv); cudaFree(db.d_tfv);
-  cudaFree(db.d_bias_eo); cudaFree(db.d_tile_blob); cudaFree(db.d_tiles); cudaFree(db.d_tile_models); cudaFree(db.d_groups);
+  cudaFree(db.d_bias_eo); cudaFree(db.d_twb); cudaFree(db.d_rwb); cudaFree(db.d_tfb); cudaFree(db.d_rfb); cudaFree(db.d_tile_blob); cudaFree(db.d_tiles); cudaFree(db.d_tile_models); cudaFree(db.d_groups);
   cudaFree(db.d_chain_first_tile); cudaFree(db.d_chain_ntiles);
 }
 

@@ -139,7 +139,7 @@ __device__ __forceinline__ bool ekey_equal(const RRow &a, const RRow &b) {
 }
 
 // R2: one thread per accepted Pfam hit rebuilds its ORF's group and replays the clan filter
-constexpr int GROUP_CAP = 96;
+constexpr int GROUP_CAP = 384;
 __global__ void r2_clan_filter(RParams p, int32_t *overflow) {
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < p.nseg; s += gridDim.x * blockDim.x) {
     if (!p.models[p.seg_model[s]].is_pfam) continue;
@@ -454,7 +454,7 @@ extern "C" int ckm_reduce(ckm_engine *e, int32_t nmodels_in, int32_t nseq_in, in
   RCUDA(cudaMemcpyAsync(&overflow, d_overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   RCUDA(cudaStreamSynchronize(st));
   cleanup();
-  if (overflow) { std::free(qa); set_error("ckm_reduce: more than 96 Pfam hits on one ORF"); return CKM_ECAPACITY; }
+  if (overflow) { std::free(qa); set_error("ckm_reduce: more than 384 Pfam hits on one ORF"); return CKM_ECAPACITY; }
   // compact the per-segment lists
   int64_t total = 0;
   for (int s = 0; s < nseg; ++s) total += mh_len[s];

@@ -175,6 +175,7 @@ static int run_stage2(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
   FilterParams p{};
   p.res = db->d_res; p.off = db->d_off; p.len = db->d_len; p.lenA = db->d_lenA; p.lenB = db->d_lenB; p.tmove_w = db->d_tmove_w;
   p.ms = m->d_scalars; p.bias_eo = m->d_bias_eo; p.rwv = m->d_rwv; p.twv = m->d_twv; p.rfv = m->d_rfv; p.tfv = m->d_tfv;
+  p.twb = m->d_twb; p.rwb = m->d_rwb; p.tfb = m->d_tfb; p.rfb = m->d_rfb;
   p.row_elems = ((m->maxM + 31) / 32) * 32 + 64;
   p.F1 = 0.02; p.F2 = 1e-3; p.F3 = 1e-5;
   p.dense_filtersc = d_filtersc; p.dense_vit = d_vit; p.dense_fwd = d_fwd; p.dense_passed = d_passed;
@@ -187,14 +188,15 @@ static int run_stage2(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
   // viterbi: a -> b
   p.in = s2.a.as<Candidate>(); p.in_count = e->d_counters + CTR_BIAS; p.in_cap = s2.cap;
   p.out = s2.b.as<Candidate>(); p.out_count = e->d_counters + CTR_VIT; p.out_cap = s2.cap;
-  if ((rc = launch_vit(p, nsm * 4, st))) return rc;
+  if ((rc = launch_vit2(p, nsm * 8, st))) return rc;      // models up to M = 512: lane-blocked register kernels
+  if ((rc = launch_vit(p, nsm * 4, st))) return rc;       // longer models: shared-memory rows
   CKM_CUDA(cudaEventRecord(e->ev[4], st));
   // forward: b -> a
   p.in = s2.b.as<Candidate>(); p.in_count = e->d_counters + CTR_VIT; p.in_cap = s2.cap;
   p.out = s2.a.as<Candidate>(); p.out_count = e->d_counters + CTR_FWD; p.out_cap = s2.cap;
   if ((rc = launch_fwd(p, nsm * 4, st))) return rc;
   CKM_CUDA(cudaEventRecord(e->ev[5], st));
-  e->stats.kernel_launches += 3;
+  e->stats.kernel_launches += 7;
   s2.fwd_list = s2.a.as<Candidate>();
   return CKM_OK;
 }

@@ -53,6 +53,7 @@ struct FilterParams {
   const int16_t *tmove_w;
   const ModelScalars *ms;
   const float *bias_eo; const int16_t *rwv; const int16_t *twv; const float *rfv; const float *tfv;
+  const uint4 *twb; const uint32_t *rwb; const float4 *tfb; const float *rfb;   // lane-blocked tables
   const Candidate *in; const int32_t *in_count; int32_t in_cap;
   Candidate *out; int32_t *out_count; int32_t out_cap;
   int32_t row_elems;                 // shared-memory elements of one DP row
@@ -63,6 +64,7 @@ struct FilterParams {
 };
 int launch_bias(const FilterParams &p, int grid, cudaStream_t st);
 int launch_vit(const FilterParams &p, int grid, cudaStream_t st);
+int launch_vit2(const FilterParams &p, int grid, cudaStream_t st);
 int launch_fwd(const FilterParams &p, int grid, cudaStream_t st);
 
 // ---- stage 5: domain definition ----
