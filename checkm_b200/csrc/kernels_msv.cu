@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(SSV_WARPS * 32, 1) ssv_kernel(SsvParams p) {
 template __global__ void ssv_kernel<4>(SsvParams);
 template __global__ void ssv_kernel<8>(SsvParams);
 template __global__ void ssv_kernel<16>(SsvParams);
+template __global__ void ssv_kernel<32>(SsvParams);
 
 int launch_ssv(int J, const SsvParams &p, int grid, size_t smem_bytes, cudaStream_t stream) {
   cudaError_t e;
@@ -196,6 +197,11 @@ int launch_ssv(int J, const SsvParams &p, int grid, size_t smem_bytes, cudaStrea
       e = cudaFuncSetAttribute(ssv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ssv<16>)");
       ssv_kernel<16><<<grid, SSV_WARPS * 32, smem_bytes, stream>>>(p);
+      break;
+    case 32:
+      e = cudaFuncSetAttribute(ssv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ssv<32>)");
+      ssv_kernel<32><<<grid, SSV_WARPS * 32, smem_bytes, stream>>>(p);
       break;
     default: set_error("unsupported tile width"); return CKM_EINVAL;
   }

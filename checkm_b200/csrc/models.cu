@@ -1,6 +1,7 @@
 // models.cu -- model database on the device: per-model score tables for the survivor stages and the packed SSV tiles.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <stdexcept>
@@ -32,15 +33,23 @@ static int tile_block_bytes_host(int J) { return KPAD * 128 * J + 768; }
 static void build_tiles(ckm_models &db, std::vector<uint8_t> &blob) {
   const int n = (int)db.models.size();
   struct Item { int model, M; };
+  // tile width policy: CKM_SSV_J = auto (4/8/16 by model length) | 8 | 16 | 32 (one width for every model)
+  const char *pol = std::getenv("CKM_SSV_J");
+  int fixedJ = 32;
+  if (pol != nullptr) { if (!std::strcmp(pol, "auto")) fixedJ = 0; else fixedJ = std::atoi(pol); }
+  if (fixedJ != 0 && fixedJ != 4 && fixedJ != 8 && fixedJ != 16 && fixedJ != 32) fixedJ = 32;
   std::vector<Item> cls[3], longm;
+  int Js[3] = {4, 8, 16};
+  int chainJ = 16;
+  if (fixedJ != 0) { Js[0] = Js[1] = Js[2] = fixedJ; chainJ = (fixedJ == 32) ? 16 : fixedJ; }   // chains must fit shared memory together
   for (int i = 0; i < n; ++i) {
     int M = db.models[i].M;
-    if (M <= 255) cls[0].push_back({i, M});
+    if (fixedJ != 0) { if (M <= 64 * fixedJ - 1) cls[0].push_back({i, M}); else longm.push_back({i, M}); }
+    else if (M <= 255) cls[0].push_back({i, M});
     else if (M <= 511) cls[1].push_back({i, M});
     else if (M <= 1023) cls[2].push_back({i, M});
     else longm.push_back({i, M});
   }
-  const int Js[3] = {4, 8, 16};
   struct HostTile { int J; std::vector<TileModel> tm; int used; int chain_prev, chain_next; };
   std::vector<HostTile> tiles;
   std::vector<std::pair<int, int>> chains;   // (first tile, ntiles)
@@ -61,19 +70,20 @@ static void build_tiles(ckm_models &db, std::vector<uint8_t> &blob) {
     }
     for (size_t t = first; t < tiles.size(); ++t) chains.push_back({(int)t, 1});
   }
+  const int chunk_cells = 64 * chainJ;
   for (const Item &it : longm) {
     int ncells = it.M + 1;                    // real cells + the mandatory padding cell
-    int nch = (ncells + 1023) / 1024;
+    int nch = (ncells + chunk_cells - 1) / chunk_cells;
     chains.push_back({(int)tiles.size(), nch});
     for (int c = 0; c < nch; ++c) {
-      HostTile ht{16, {}, 64, c > 0, c + 1 < nch};
+      HostTile ht{chainJ, {}, 64, c > 0, c + 1 < nch};
       ht.tm.push_back({it.model, 0, 64, c});
       tiles.push_back(ht);
       tile_class.push_back(3);
     }
   }
   // groups: consecutive chains of equal J up to the shared-memory budget
-  const int64_t cap = 196608;
+  const int64_t cap = 200000;
   db.tiles.clear(); db.tile_models.clear(); db.groups.clear(); db.chain_first_tile.clear(); db.chain_ntiles.clear();
   int64_t off = 0;
   for (size_t t = 0; t < tiles.size(); ++t) {
@@ -90,7 +100,7 @@ static void build_tiles(ckm_models &db, std::vector<uint8_t> &blob) {
     for (size_t c = 0; c < chains.size(); ++c) {
       int t0 = chains[c].first, nt = chains[c].second, J = tiles[t0].J;
       int64_t need = (int64_t)nt * tile_block_bytes_host(J);
-      if (need > cap) throw std::runtime_error("model " + db.models[tiles[t0].tm[0].model].name + " is too long for the SSV tiles (M >= 3072)");
+      if (need > cap) throw std::runtime_error("model " + db.models[tiles[t0].tm[0].model].name + " is too long for the SSV tiles");
       if (open && (g.J != J || gbytes + need > cap)) { g.table_bytes = gbytes; db.groups.push_back(g); open = false; }
       if (!open) { g = TileGroup{}; g.J = J; g.first_tile = t0; g.ntiles = 0; g.nchains = 0; g.first_chain = (int)c; g.table_off = db.tiles[t0].table_off; gbytes = 0; open = true; }
       g.ntiles += nt; g.nchains += 1; gbytes += need;
@@ -119,7 +129,7 @@ static void build_tiles(ckm_models &db, std::vector<uint8_t> &blob) {
         SM[slot] = (int)j;
         const int lane = slot & 31, half = slot >> 5;
         for (int q = 0; q < J; ++q) {
-          const int k = tm.chunk * 1024 + sl * J + q + 1;      // model position of this cell
+          const int k = tm.chunk * 64 * J + sl * J + q + 1;    // model position of this cell
           if (k > m.M) continue;
           for (int x = 0; x < KP; ++x) {
             const int d = (int)m.bias_b - (int)m.rbv[(size_t)x * W1 + k];

@@ -25,7 +25,7 @@ struct DevBuf {
   template <class T> T *as() { return reinterpret_cast<T *>(p); }
 };
 
-enum { CTR_UNIT4 = 0, CTR_UNIT8, CTR_UNIT16, CTR_CAND, CTR_MSV, CTR_BIAS, CTR_VIT, CTR_FWD, CTR_ENV, CTR_DOM, CTR_N = 32 };
+enum { CTR_UNIT4 = 0, CTR_UNIT8, CTR_UNIT16, CTR_UNIT32, CTR_CAND, CTR_MSV, CTR_BIAS, CTR_VIT, CTR_FWD, CTR_ENV, CTR_DOM, CTR_N = 32 };
 
 struct ActiveMasks {
   DevBuf tile_active, model_active, model_slot;
@@ -101,18 +101,18 @@ static int run_stage1(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
   const int64_t bnd_stride = ((int64_t)db->maxL + 31) / 16 * 16;
   if (need_bnd) { if ((rc = s1.bnd.alloc((size_t)nsm * SSV_WARPS_HOST * 2 * bnd_stride * sizeof(int16_t)))) return rc; }
   // group lists per J
-  std::vector<int32_t> gl[3];
-  for (size_t g = 0; g < m->groups.size(); ++g) gl[m->groups[g].J == 4 ? 0 : (m->groups[g].J == 8 ? 1 : 2)].push_back((int32_t)g);
+  std::vector<int32_t> gl[4];
+  for (size_t g = 0; g < m->groups.size(); ++g) gl[m->groups[g].J == 4 ? 0 : (m->groups[g].J == 8 ? 1 : (m->groups[g].J == 16 ? 2 : 3))].push_back((int32_t)g);
   std::vector<int32_t> flat;
-  size_t goff[3];
-  for (int c = 0; c < 3; ++c) { goff[c] = flat.size(); flat.insert(flat.end(), gl[c].begin(), gl[c].end()); }
+  size_t goff[4];
+  for (int c = 0; c < 4; ++c) { goff[c] = flat.size(); flat.insert(flat.end(), gl[c].begin(), gl[c].end()); }
   if ((rc = s1.glist.alloc(sizeof(int32_t) * std::max<size_t>(flat.size(), 1)))) return rc;
   if (!flat.empty()) CKM_CUDA(cudaMemcpyAsync(s1.glist.p, flat.data(), sizeof(int32_t) * flat.size(), cudaMemcpyHostToDevice, st));
   CKM_CUDA(cudaStreamSynchronize(st));
 
   CKM_CUDA(cudaEventRecord(e->ev[0], st));
-  const int Js[3] = {4, 8, 16};
-  for (int c = 0; c < 3; ++c) {
+  const int Js[4] = {4, 8, 16, 32};
+  for (int c = 0; c < 4; ++c) {
     if (gl[c].empty() || db->nseq == 0) continue;
     SsvParams p{};
     p.res = db->d_res; p.off = db->d_off; p.len = db->d_len; p.bin = db->d_bin;
