@@ -6,6 +6,7 @@
 #include "device_utils.cuh"
 #include "stages.hpp"
 #include "fwdback.cuh"
+#include "domdef_common.cuh"
 
 namespace ckm {
 
@@ -29,6 +30,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) regions_kernel(DomdefParams p)
     const PairWork pw = p.pairs[pi];
     const int L = pw.L;
     const ModelScalars ms = p.ms[pw.model];
+    if (p.use_blk && ms.vq != 0) continue;            // handled by regions2_kernel<Q>
     const FwdModel fm = make_fwd_model(p, ms);
     const uint8_t *res = p.res + p.off[pw.seq];
     const Specials sp = make_specials(L, true);
@@ -38,42 +40,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) regions_kernel(DomdefParams p)
     __syncwarp();
     backward_rows<false>(fm, res, L, sp, rowM, rowI, rowD, lane, xf, xb, nullptr);
     __syncwarp();
-    const float scaleproduct = __fdiv_rn(1.0f, xb[X_N]);
-    for (int i = lane; i <= L; i += 32) {
-      n2sc[i] = 0.0f;
-      if (i == 0) { btot[0] = 0.0f; etot[0] = 0.0f; mocc[0] = 0.0f; continue; }
-      const float *f0 = xf + (int64_t)(i - 1) * X_NX, *f1 = xf + (int64_t)i * X_NX;
-      const float *b0 = xb + (int64_t)(i - 1) * X_NX, *b1 = xb + (int64_t)i * X_NX;
-      btot[i] = (f0[X_B] * b0[X_B]) * f0[X_SCALE] * scaleproduct;      // per-row terms; prefix-summed below
-      etot[i] = (f1[X_E] * b1[X_E]) * f1[X_SCALE] * scaleproduct;
-      float njcp;
-      njcp = f0[X_N] * b1[X_N] * sp.nloop * scaleproduct;
-      njcp += f0[X_J] * b1[X_J] * sp.nloop * scaleproduct;
-      njcp += f0[X_C] * b1[X_C] * sp.nloop * scaleproduct;
-      mocc[i] = 1.0f - njcp;
-    }
-    __syncwarp();
-    if (lane == 0) {
-      float bt = 0.0f, et = 0.0f;
-      for (int i = 1; i <= L; ++i) { bt = bt + btot[i]; et = et + etot[i]; btot[i] = bt; etot[i] = et; }
-      int i = -1; bool triggered = false;
-      for (int j = 1; j <= L; ++j) {
-        if (!triggered) {
-          if (mocc[j] - (btot[j] - btot[j - 1]) < 0.10f) i = j;
-          else if (i == -1) i = j;
-          if (mocc[j] >= 0.25f) triggered = true;
-        } else if (mocc[j] - (etot[j] - etot[j - 1]) < 0.10f) {
-          float mx = -1.0f;
-          for (int z = i; z <= j; ++z) {
-            const float a = etot[z] - etot[i - 1], b = btot[j] - btot[z - 1];
-            mx = fmaxf(mx, fminf(a, b));
-          }
-          const int pos = atomicAdd(p.region_count, 1);
-          if (pos < p.region_cap) { Region r; r.pair = pi; r.i = i; r.j = j; r.multi = (mx >= 0.20f) ? 1 : 0; p.regions[pos] = r; }
-          i = -1; triggered = false;
-        }
-      }
-    }
+    regions_tail(p, pi, L, sp, xf, xb, btot, etot, mocc, n2sc, lane);
     __syncwarp();
   }
 }
@@ -81,7 +48,6 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) regions_kernel(DomdefParams p)
 // ------------------------------------------------------------------------------------------------
 // 5b: rescore one envelope
 // ------------------------------------------------------------------------------------------------
-enum { ST_M = 1, ST_D, ST_I, ST_S, ST_N, ST_B, ST_E, ST_C, ST_T, ST_J };
 
 __global__ void __launch_bounds__(FWD_WARPS * 32) envelope_kernel(DomdefParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -92,6 +58,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) envelope_kernel(DomdefParams p
     const Envelope env = p.envs[ei];
     const PairWork pw = p.pairs[env.pair];
     const ModelScalars ms = p.ms[pw.model];
+    if (p.use_blk && ms.vq != 0) continue;            // handled by envelope2_kernel<Q>
     const FwdModel fm = make_fwd_model(p, ms);
     const int M = fm.M, Mpad = fm.Mpad, Ld = env.j - env.i + 1, nchunk = (M + 31) >> 5;
     const uint8_t *res = p.res + p.off[pw.seq] + (env.i - 1);

@@ -162,9 +162,20 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) vit_kernel(FilterParams p) {
 // and the 8 transitions of each position), so a row costs two boundary shuffles, two warp reductions and -- only when
 // the lazy-F test says a D->D path could matter -- one max-plus scan across the lanes.  Same int16 semantics as above.
 // ------------------------------------------------------------------------------------------------
-template <int Q>
+struct Tr8 { int bm, mm, im, dm, md, mi, ii, dd; };
+__device__ __forceinline__ Tr8 unpack_tr(const uint4 t) {
+  Tr8 r;
+  r.bm = (int16_t)(t.x & 0xffff); r.mm = (int16_t)(t.x >> 16); r.im = (int16_t)(t.y & 0xffff); r.dm = (int16_t)(t.y >> 16);
+  r.md = (int16_t)(t.z & 0xffff); r.mi = (int16_t)(t.z >> 16); r.ii = (int16_t)(t.w & 0xffff); r.dd = (int16_t)(t.w >> 16);
+  return r;
+}
+
+// TSMEM: keep the (packed) transitions of the warp's model in shared memory instead of registers (Q = 32, M <= 1024)
+template <int Q, bool TSMEM>
 __global__ void __launch_bounds__(128) vit2_kernel(FilterParams p) {
+  extern __shared__ __align__(16) uint8_t vsm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  uint4 *tws = reinterpret_cast<uint4 *>(vsm) + (size_t)warp * Q * 32;
   const int n = min(*p.in_count, p.in_cap);
   for (int c = blockIdx.x * wpb + warp; c < n; c += gridDim.x * wpb) {
     Candidate cd = p.in[c];
@@ -174,14 +185,17 @@ __global__ void __launch_bounds__(128) vit2_kernel(FilterParams p) {
     const int s = cd.seq, L = p.len[s];
     bool pass = true;
     if (cd.P > p.F2) {
-      // transitions of my Q positions, unpacked once: {BM, MM, IM, DM, MD, MI, II, DD}
-      int tr[Q][8];
+      // transitions of my Q positions {BM, MM, IM, DM, MD, MI, II, DD}: registers, or shared memory for the widest class
+      Tr8 trr[TSMEM ? 1 : Q];
+      if (TSMEM) {
+        __syncwarp();
+        for (int q = 0; q < Q; ++q) tws[q * 32 + lane] = __ldg(p.twb + (ms.blk_off + q) * 32 + lane);
+        __syncwarp();
+      } else {
 #pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        const uint4 t = __ldg(p.twb + (ms.blk_off + q) * 32 + lane);
-        tr[q][0] = (int16_t)(t.x & 0xffff); tr[q][1] = (int16_t)(t.x >> 16); tr[q][2] = (int16_t)(t.y & 0xffff); tr[q][3] = (int16_t)(t.y >> 16);
-        tr[q][4] = (int16_t)(t.z & 0xffff); tr[q][5] = (int16_t)(t.z >> 16); tr[q][6] = (int16_t)(t.w & 0xffff); tr[q][7] = (int16_t)(t.w >> 16);
+        for (int q = 0; q < Q; ++q) trr[q] = unpack_tr(__ldg(p.twb + (ms.blk_off + q) * 32 + lane));
       }
+#define TRQ(q) (TSMEM ? unpack_tr(tws[(q) * 32 + lane]) : trr[TSMEM ? 0 : (q)])
       const uint32_t *rwb = p.rwb + ms.blk_off * 32 * (KPAD / 2) + lane;
       int Mx[Q], Ix[Q], Dx[Q];
 #pragma unroll
@@ -211,14 +225,15 @@ __global__ void __launch_bounds__(128) vit2_kernel(FilterParams p) {
 #pragma unroll
           for (int q = Q - 1; q >= 0; --q) {
             const int pm = (q > 0) ? Mx[q - 1] : pm_in, pi = (q > 0) ? Ix[q - 1] : pi_in, pd = (q > 0) ? Dx[q - 1] : bd;
-            int sv = __viaddmax_s32(xB, tr[q][0], -32768);
-            sv = __viaddmax_s32(pm, tr[q][1], sv);
-            sv = __viaddmax_s32(pi, tr[q][2], sv);
-            sv = __viaddmax_s32(pd, tr[q][3], sv);
+            const Tr8 t = TRQ(q);
+            int sv = __viaddmax_s32(xB, t.bm, -32768);
+            sv = __viaddmax_s32(pm, t.mm, sv);
+            sv = __viaddmax_s32(pi, t.im, sv);
+            sv = __viaddmax_s32(pd, t.dm, sv);
             const int e = (q & 1) ? ((int)e2[q >> 1] >> 16) : (int)(int16_t)(e2[q >> 1] & 0xffffu);
             sv = min(__viaddmax_s32(sv, e, -32768), 32767);
-            const int nI = __viaddmax_s32(Ix[q], tr[q][6], __viaddmax_s32(Mx[q], tr[q][5], -32768));
-            md[q] = __viaddmax_s32(sv, tr[q][4], -32768);
+            const int nI = __viaddmax_s32(Ix[q], t.ii, __viaddmax_s32(Mx[q], t.mi, -32768));
+            md[q] = __viaddmax_s32(sv, t.md, -32768);
             xEl = max(xEl, sv); dml = max(dml, md[q]);
             Mx[q] = sv; Ix[q] = nI;
           }
@@ -233,7 +248,7 @@ __global__ void __launch_bounds__(128) vit2_kernel(FilterParams p) {
             // full D->D: composite of my block f(d) = max(Bb, d + Tb), exclusive max-plus scan across lanes
             int Bb = -32768, Tb = 0;
 #pragma unroll
-            for (int q = 0; q < Q; ++q) { Bb = max(md[q], Bb + tr[q][7]); Bb = max(Bb, -32768); Tb = max(Tb + tr[q][7], -(1 << 24)); }
+            for (int q = 0; q < Q; ++q) { const int tdd = TRQ(q).dd; Bb = max(md[q], Bb + tdd); Bb = max(Bb, -32768); Tb = max(Tb + tdd, -(1 << 24)); }
             int Bs = Bb, Ts = Tb;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -244,7 +259,7 @@ __global__ void __launch_bounds__(128) vit2_kernel(FilterParams p) {
             if (lane == 0) din = -32768;
             int d = din;
 #pragma unroll
-            for (int q = 0; q < Q; ++q) { Dx[q] = d; d = max(max(md[q], d + tr[q][7]), -32768); }
+            for (int q = 0; q < Q; ++q) { Dx[q] = d; d = max(max(md[q], d + TRQ(q).dd), -32768); }
           } else {
             // lazy F: no D->D path can beat entering from B; keep the M->D partials only
             int din = __shfl_up_sync(0xffffffffu, md[Q - 1], 1);
@@ -274,6 +289,7 @@ __global__ void __launch_bounds__(128) vit2_kernel(FilterParams p) {
       if (pos < p.out_cap) p.out[pos] = cd;
       if (p.dense_passed != nullptr) atomicOr_u8(p.dense_passed, (int64_t)p.model_slot[m] * p.nseq + s, 4);
     }
+#undef TRQ
   }
 }
 
@@ -290,6 +306,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) fwd_kernel(FilterParams p) {
     Candidate cd = p.in[c];
     const int s = cd.seq, m = cd.model, L = p.len[s];
     const ModelScalars ms = p.ms[m];
+    if (p.use_blk && ms.vq != 0) continue;            // handled by fwd2_kernel<Q>
     const uint8_t *res = p.res + p.off[s];
     FwdModel fm;
     fm.M = ms.M; fm.Mpad = ms.Mpad;
@@ -320,11 +337,15 @@ int launch_bias(const FilterParams &p, int grid, cudaStream_t st) {
   return e == cudaSuccess ? CKM_OK : cuda_fail(e, "bias_kernel launch");
 }
 int launch_vit2(const FilterParams &p, int grid, cudaStream_t st) {
-  vit2_kernel<2><<<grid, 128, 0, st>>>(p);
-  vit2_kernel<4><<<grid, 128, 0, st>>>(p);
-  vit2_kernel<8><<<grid, 128, 0, st>>>(p);
-  vit2_kernel<16><<<grid, 128, 0, st>>>(p);
-  cudaError_t e = cudaGetLastError();
+  vit2_kernel<2, false><<<grid, 128, 0, st>>>(p);
+  vit2_kernel<4, false><<<grid, 128, 0, st>>>(p);
+  vit2_kernel<8, false><<<grid, 128, 0, st>>>(p);
+  vit2_kernel<16, false><<<grid, 128, 0, st>>>(p);
+  const int smem32 = 4 * 32 * 32 * (int)sizeof(uint4);
+  cudaError_t e = cudaFuncSetAttribute(vit2_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(vit2<32>)");
+  vit2_kernel<32, true><<<grid, 128, smem32, st>>>(p);
+  e = cudaGetLastError();
   return e == cudaSuccess ? CKM_OK : cuda_fail(e, "vit2_kernel launch");
 }
 int launch_vit(const FilterParams &p, int grid, cudaStream_t st) {

@@ -2,6 +2,7 @@
 // stream and assembles the hit table.  Replaces the body of `hmmsearch` behind checkm/hmmer.py:61-74.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "engine.hpp"
@@ -25,6 +26,7 @@ struct DevBuf {
   template <class T> T *as() { return reinterpret_cast<T *>(p); }
 };
 
+static bool use_blocked_kernels();
 enum { CTR_UNIT4 = 0, CTR_UNIT8, CTR_UNIT16, CTR_UNIT32, CTR_CAND, CTR_MSV, CTR_BIAS, CTR_VIT, CTR_FWD, CTR_ENV, CTR_DOM, CTR_N = 32 };
 
 struct ActiveMasks {
@@ -178,6 +180,7 @@ static int run_stage2(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
   p.twb = m->d_twb; p.rwb = m->d_rwb; p.tfb = m->d_tfb; p.rfb = m->d_rfb;
   p.row_elems = ((m->maxM + 31) / 32) * 32 + 64;
   p.F1 = 0.02; p.F2 = 1e-3; p.F3 = 1e-5;
+  p.use_blk = use_blocked_kernels() ? 1 : 0;
   p.dense_filtersc = d_filtersc; p.dense_vit = d_vit; p.dense_fwd = d_fwd; p.dense_passed = d_passed;
   p.model_slot = am.model_slot.as<int32_t>(); p.nseq = db->nseq;
   // bias: pass list (stage 1) -> a
@@ -194,9 +197,10 @@ static int run_stage2(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
   // forward: b -> a
   p.in = s2.b.as<Candidate>(); p.in_count = e->d_counters + CTR_VIT; p.in_cap = s2.cap;
   p.out = s2.a.as<Candidate>(); p.out_count = e->d_counters + CTR_FWD; p.out_cap = s2.cap;
+  if (p.use_blk) { if ((rc = launch_fwd2(p, nsm * 8, st))) return rc; }
   if ((rc = launch_fwd(p, nsm * 4, st))) return rc;
   CKM_CUDA(cudaEventRecord(e->ev[5], st));
-  e->stats.kernel_launches += 7;
+  e->stats.kernel_launches += 8 + (p.use_blk ? 5 : 0);
   s2.fwd_list = s2.a.as<Candidate>();
   return CKM_OK;
 }
@@ -258,6 +262,9 @@ namespace ckm {
 constexpr int X_NX_HOST = 6;
 int run_ensembles(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, DomdefParams &p, const std::vector<PairWork> &pairs,
                   const std::vector<Region> &regs, const std::vector<int> &multi_idx, std::vector<std::vector<Envelope>> &out);
+
+static bool use_blocked_kernels() { const char *v = std::getenv("CKM_BLK"); return !(v != nullptr && v[0] == '0'); }
+static int vq_of(int M) { return (M <= 64) ? 2 : (M <= 128) ? 4 : (M <= 256) ? 8 : (M <= 512) ? 16 : (M <= 1024) ? 32 : 0; }
 
 static std::vector<float> &logsum_table() {
   static std::vector<float> t;
@@ -344,6 +351,8 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
     p.regions = dregions.as<Region>(); p.region_count = e->d_counters + CTR_ENV; p.region_cap = region_cap;
     p.logsum_tbl = dtbl.as<float>();
     p.row_elems = ((m->maxM + 31) / 32) * 32 + 64;
+    p.tfb = m->d_tfb; p.rfb = m->d_rfb; p.use_blk = use_blocked_kernels() ? 1 : 0;
+    if (p.use_blk) { if ((rc = launch_regions2(p, std::min(nsm * 8, (npairs + 3) / 4), st))) return rc; e->stats.kernel_launches += 5; }
     if ((rc = launch_regions(p, std::min(nsm * 4, (npairs + FWD_WARPS - 1) / FWD_WARPS), st))) return rc;
     e->stats.kernel_launches++;
     int32_t nreg = 0;
@@ -379,7 +388,9 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
       for (size_t i = 0; i < envs.size(); ++i) {
         const PairWork &pw = pairs[envs[i].pair];
         const int64_t Ld = envs[i].j - envs[i].i + 1, Mpad = ((m->models[pw.model].M + 1) + 31) / 32 * 32 + 32;
-        need[i] = 2 * (Ld + 1) * 3 * Mpad + (Ld + 1) * 15 + 64;
+        const int64_t vq = p.use_blk ? vq_of(m->models[pw.model].M) : 0;
+        const int64_t width = vq ? 32 * vq : Mpad;
+        need[i] = 2 * (Ld + 1) * 3 * width + (Ld + 1) * 15 + 64;
       }
       size_t free_b = 0, total_b = 0;
       cudaMemGetInfo(&free_b, &total_b);
@@ -394,6 +405,7 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
         if (tot > cur_alloc) { if ((rc = dscratch.alloc(sizeof(float) * (size_t)tot))) return rc; cur_alloc = tot; }
         CKM_CUDA(cudaMemcpyAsync(denvs.as<Envelope>() + w0, envs.data() + w0, sizeof(Envelope) * (w1 - w0), cudaMemcpyHostToDevice, st));
         p.envs = denvs.as<Envelope>(); p.env_begin = (int32_t)w0; p.env_end = (int32_t)w1; p.scratch = dscratch.as<float>(); p.doms = ddoms.as<DomainOut>();
+        if (p.use_blk) { if ((rc = launch_envelopes2(p, std::min<int>(nsm * 8, (int)((w1 - w0 + 3) / 4)), st))) return rc; e->stats.kernel_launches += 5; }
         if ((rc = launch_envelopes(p, std::min<int>(nsm * 4, (int)((w1 - w0 + FWD_WARPS - 1) / FWD_WARPS)), st))) return rc;
         e->stats.kernel_launches++;
         CKM_CUDA(cudaStreamSynchronize(st));

@@ -58,6 +58,7 @@ struct FilterParams {
   Candidate *out; int32_t *out_count; int32_t out_cap;
   int32_t row_elems;                 // shared-memory elements of one DP row
   double F1, F2, F3;
+  int32_t use_blk;                   // 1: models with a blocked class go to the *2 kernels
   // optional dense outputs for parity tests
   float *dense_filtersc, *dense_vit, *dense_fwd; uint8_t *dense_passed;
   const int32_t *model_slot; int32_t nseq;
@@ -94,9 +95,14 @@ struct DomdefParams {
   DomainOut *doms; HitOut *hits;
   const float *logsum_tbl;
   int32_t row_elems;
+  const float4 *tfb; const float *rfb;   // lane-blocked tables
+  int32_t use_blk;                       // 1: models with a blocked class go to the *2 kernels
 };
 int launch_regions(const DomdefParams &p, int grid, cudaStream_t st);
 int launch_envelopes(const DomdefParams &p, int grid, cudaStream_t st);
 int launch_scores(const DomdefParams &p, int grid, cudaStream_t st);
+int launch_fwd2(const FilterParams &p, int grid, cudaStream_t st);
+int launch_regions2(const DomdefParams &p, int grid, cudaStream_t st);
+int launch_envelopes2(const DomdefParams &p, int grid, cudaStream_t st);
 
 }  // namespace ckm
