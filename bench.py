@@ -286,13 +286,22 @@ def main():
         dist.all_gather_into_tensor(gather_buf.view(-1), mine)        # NCCL all-gather of the fixed-width QA rows (config #4)
         return gather_buf
 
+    host_ms = {'flush': 0.0, 'search': 0.0, 'reduce': 0.0, 'gather': 0.0}
+
     def step_resident(i):
         batch = batches[i % 2]
+        t0 = time.perf_counter()
         flush_buf.zero_()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
         hits = eng.search(models, batch['db'])
         st = eng.stats()
+        t2 = time.perf_counter()
         rows, nmh = reduce_hits(batch, hits)
+        t3 = time.perf_counter()
         gather(rows)
+        t4 = time.perf_counter()
+        host_ms['flush'] += 1e3 * (t1 - t0); host_ms['search'] += 1e3 * (t2 - t1); host_ms['reduce'] += 1e3 * (t3 - t2); host_ms['gather'] += 1e3 * (t4 - t3)
         return hits, st, rows
 
     def step_e2e(i):
@@ -315,6 +324,8 @@ def main():
 
     for i in range(args.warmup):
         step_resident(i)
+    for k_ in host_ms:
+        host_ms[k_] = 0.0
     sampler = ClockSampler(local)
     sampler.start()
     sync()
@@ -377,6 +388,7 @@ def main():
             "gcups": {"real_cells_per_step": real_cells, "tile_cells_per_step": cells / args.steps, "ssv_gcups_real": real_cells / ssv_s / 1e9,
                       "ssv_gcups_tile": cells / args.steps / ssv_s / 1e9, "smem_bound_gcups_at_1.9GHz": 148 * 51.2 * 1.9,
                       "stage_ms_per_step": {"ssv": ssv_ms / args.steps, "msv_exact": msv_ms / args.steps, "bias+vit+fwd+domdef": other_ms / args.steps,
+                                            "wall_ms_per_step": {k_: v_ / args.steps for k_, v_ in host_ms.items()},
                                             "last_step": {"bias": st.ms_bias, "vit": st.ms_vit, "fwd": st.ms_fwd, "domdef": st.ms_domdef, "total": st.ms_total}}},
             "cascade": {"pairs": int(st.n_pairs), "ssv_cand": int(st.n_ssv_cand), "past_msv": int(st.n_past_msv), "past_bias": int(st.n_past_bias),
                         "past_vit": int(st.n_past_vit), "past_fwd": int(st.n_past_fwd), "rows": int(st.n_reported)},

@@ -54,6 +54,7 @@ void ckm_destroy(ckm_engine *e) {
   for (auto &ev : e->ev) cudaEventDestroy(ev);
   cudaFree(e->d_counters);
   cudaFree(e->d_scratch);
+  for (auto &ent : e->pool) cudaFree(ent.first);
   cudaStreamDestroy(e->stream);
   delete e;
 }

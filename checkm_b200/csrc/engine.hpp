@@ -134,7 +134,8 @@ struct ckm_engine {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[16];
   ckm_stats stats;
-  // reusable device scratch
+  // grow-only device buffer cache: slot -> (pointer, bytes); search/reduce workspaces are reused across calls
+  std::vector<std::pair<void *, size_t>> pool;
   void   *d_scratch = nullptr; size_t scratch_bytes = 0;
   int32_t *d_counters = nullptr;   // small array of device counters
 };

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(BLK_WARPS * 32) envelope2_kernel(DomdefParams 
       for (int q = 0; q < Q; ++q) {
         const float pm = fr[q * 32] * br[q * 32] * totr;
         const float pi = fr[(2 * Q + q) * 32] * br[(2 * Q + q) * 32] * totr;
-        br[q * 32] = pm; br[(Q + q) * 32] = 0.0f; br[(2 * Q + q) * 32] = pi;
+        br[q * 32] = pm; br[(2 * Q + q) * 32] = pi;        // the D plane is never read again
         em[q] = (r == 1) ? pm : em[q] + pm;
         ein[q] = (r == 1) ? pi : ein[q] + pi;
       }
@@ -353,30 +353,45 @@ static int launch_one(KF kern, const P &p, int grid, size_t extra, cudaStream_t 
 
 int launch_fwd2(const FilterParams &p, int grid, cudaStream_t st) {
   int rc;
-  if ((rc = launch_one<2, false>(fwd2_kernel<2, false>, p, grid, 0, st, "fwd2<2>"))) return rc;
-  if ((rc = launch_one<4, false>(fwd2_kernel<4, false>, p, grid, 0, st, "fwd2<4>"))) return rc;
-  if ((rc = launch_one<8, false>(fwd2_kernel<8, false>, p, grid, 0, st, "fwd2<8>"))) return rc;
-  if ((rc = launch_one<16, true>(fwd2_kernel<16, true>, p, grid, 0, st, "fwd2<16>"))) return rc;
-  if ((rc = launch_one<32, true>(fwd2_kernel<32, true>, p, grid, 0, st, "fwd2<32>"))) return rc;
+  if ((rc = launch_one<2, false>(fwd2_kernel<2, false>, p, grid, 0, st, "fwd2_kernel<2>"))) return rc;
+  if ((rc = launch_one<4, false>(fwd2_kernel<4, false>, p, grid, 0, st, "fwd2_kernel<4>"))) return rc;
+  if ((rc = launch_one<6, false>(fwd2_kernel<6, false>, p, grid, 0, st, "fwd2_kernel<6>"))) return rc;
+  if ((rc = launch_one<8, false>(fwd2_kernel<8, false>, p, grid, 0, st, "fwd2_kernel<8>"))) return rc;
+  if ((rc = launch_one<12, true>(fwd2_kernel<12, true>, p, grid, 0, st, "fwd2_kernel<12>"))) return rc;
+  if ((rc = launch_one<16, true>(fwd2_kernel<16, true>, p, grid, 0, st, "fwd2_kernel<16>"))) return rc;
+  if ((rc = launch_one<20, true>(fwd2_kernel<20, true>, p, grid, 0, st, "fwd2_kernel<20>"))) return rc;
+  if ((rc = launch_one<24, true>(fwd2_kernel<24, true>, p, grid, 0, st, "fwd2_kernel<24>"))) return rc;
+  if ((rc = launch_one<28, true>(fwd2_kernel<28, true>, p, grid, 0, st, "fwd2_kernel<28>"))) return rc;
+  if ((rc = launch_one<32, true>(fwd2_kernel<32, true>, p, grid, 0, st, "fwd2_kernel<32>"))) return rc;
   return CKM_OK;
 }
 int launch_regions2(const DomdefParams &p, int grid, cudaStream_t st) {
   int rc;
-  if ((rc = launch_one<2, false>(regions2_kernel<2, false>, p, grid, 0, st, "regions2<2>"))) return rc;
-  if ((rc = launch_one<4, false>(regions2_kernel<4, false>, p, grid, 0, st, "regions2<4>"))) return rc;
-  if ((rc = launch_one<8, false>(regions2_kernel<8, false>, p, grid, 0, st, "regions2<8>"))) return rc;
-  if ((rc = launch_one<16, true>(regions2_kernel<16, true>, p, grid, 0, st, "regions2<16>"))) return rc;
-  if ((rc = launch_one<32, true>(regions2_kernel<32, true>, p, grid, 0, st, "regions2<32>"))) return rc;
+  if ((rc = launch_one<2, false>(regions2_kernel<2, false>, p, grid, 0, st, "regions2_kernel<2>"))) return rc;
+  if ((rc = launch_one<4, false>(regions2_kernel<4, false>, p, grid, 0, st, "regions2_kernel<4>"))) return rc;
+  if ((rc = launch_one<6, false>(regions2_kernel<6, false>, p, grid, 0, st, "regions2_kernel<6>"))) return rc;
+  if ((rc = launch_one<8, false>(regions2_kernel<8, false>, p, grid, 0, st, "regions2_kernel<8>"))) return rc;
+  if ((rc = launch_one<12, true>(regions2_kernel<12, true>, p, grid, 0, st, "regions2_kernel<12>"))) return rc;
+  if ((rc = launch_one<16, true>(regions2_kernel<16, true>, p, grid, 0, st, "regions2_kernel<16>"))) return rc;
+  if ((rc = launch_one<20, true>(regions2_kernel<20, true>, p, grid, 0, st, "regions2_kernel<20>"))) return rc;
+  if ((rc = launch_one<24, true>(regions2_kernel<24, true>, p, grid, 0, st, "regions2_kernel<24>"))) return rc;
+  if ((rc = launch_one<28, true>(regions2_kernel<28, true>, p, grid, 0, st, "regions2_kernel<28>"))) return rc;
+  if ((rc = launch_one<32, true>(regions2_kernel<32, true>, p, grid, 0, st, "regions2_kernel<32>"))) return rc;
   return CKM_OK;
 }
 int launch_envelopes2(const DomdefParams &p, int grid, cudaStream_t st) {
   int rc;
   const size_t extra = BLK_WARPS * 32 * sizeof(float);
-  if ((rc = launch_one<2, false>(envelope2_kernel<2, false>, p, grid, extra, st, "envelope2<2>"))) return rc;
-  if ((rc = launch_one<4, false>(envelope2_kernel<4, false>, p, grid, extra, st, "envelope2<4>"))) return rc;
-  if ((rc = launch_one<8, false>(envelope2_kernel<8, false>, p, grid, extra, st, "envelope2<8>"))) return rc;
-  if ((rc = launch_one<16, true>(envelope2_kernel<16, true>, p, grid, extra, st, "envelope2<16>"))) return rc;
-  if ((rc = launch_one<32, true>(envelope2_kernel<32, true>, p, grid, extra, st, "envelope2<32>"))) return rc;
+  if ((rc = launch_one<2, false>(envelope2_kernel<2, false>, p, grid, extra, st, "envelope2_kernel<2>"))) return rc;
+  if ((rc = launch_one<4, false>(envelope2_kernel<4, false>, p, grid, extra, st, "envelope2_kernel<4>"))) return rc;
+  if ((rc = launch_one<6, false>(envelope2_kernel<6, false>, p, grid, extra, st, "envelope2_kernel<6>"))) return rc;
+  if ((rc = launch_one<8, false>(envelope2_kernel<8, false>, p, grid, extra, st, "envelope2_kernel<8>"))) return rc;
+  if ((rc = launch_one<12, true>(envelope2_kernel<12, true>, p, grid, extra, st, "envelope2_kernel<12>"))) return rc;
+  if ((rc = launch_one<16, true>(envelope2_kernel<16, true>, p, grid, extra, st, "envelope2_kernel<16>"))) return rc;
+  if ((rc = launch_one<20, true>(envelope2_kernel<20, true>, p, grid, extra, st, "envelope2_kernel<20>"))) return rc;
+  if ((rc = launch_one<24, true>(envelope2_kernel<24, true>, p, grid, extra, st, "envelope2_kernel<24>"))) return rc;
+  if ((rc = launch_one<28, true>(envelope2_kernel<28, true>, p, grid, extra, st, "envelope2_kernel<28>"))) return rc;
+  if ((rc = launch_one<32, true>(envelope2_kernel<32, true>, p, grid, extra, st, "envelope2_kernel<32>"))) return rc;
   return CKM_OK;
 }
 

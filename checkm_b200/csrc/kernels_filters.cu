@@ -337,14 +337,17 @@ int launch_bias(const FilterParams &p, int grid, cudaStream_t st) {
   return e == cudaSuccess ? CKM_OK : cuda_fail(e, "bias_kernel launch");
 }
 int launch_vit2(const FilterParams &p, int grid, cudaStream_t st) {
+  cudaError_t e;
   vit2_kernel<2, false><<<grid, 128, 0, st>>>(p);
   vit2_kernel<4, false><<<grid, 128, 0, st>>>(p);
+  vit2_kernel<6, false><<<grid, 128, 0, st>>>(p);
   vit2_kernel<8, false><<<grid, 128, 0, st>>>(p);
-  vit2_kernel<16, false><<<grid, 128, 0, st>>>(p);
-  const int smem32 = 4 * 32 * 32 * (int)sizeof(uint4);
-  cudaError_t e = cudaFuncSetAttribute(vit2_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(vit2<32>)");
-  vit2_kernel<32, true><<<grid, 128, smem32, st>>>(p);
+  { const int sm = 4 * 12 * 32 * (int)sizeof(uint4); if (sm > 48 * 1024) { e = cudaFuncSetAttribute(vit2_kernel<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(vit2)"); } vit2_kernel<12, true><<<grid, 128, sm, st>>>(p); }
+  { const int sm = 4 * 16 * 32 * (int)sizeof(uint4); if (sm > 48 * 1024) { e = cudaFuncSetAttribute(vit2_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(vit2)"); } vit2_kernel<16, true><<<grid, 128, sm, st>>>(p); }
+  { const int sm = 4 * 20 * 32 * (int)sizeof(uint4); if (sm > 48 * 1024) { e = cudaFuncSetAttribute(vit2_kernel<20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(vit2)"); } vit2_kernel<20, true><<<grid, 128, sm, st>>>(p); }
+  { const int sm = 4 * 24 * 32 * (int)sizeof(uint4); if (sm > 48 * 1024) { e = cudaFuncSetAttribute(vit2_kernel<24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(vit2)"); } vit2_kernel<24, true><<<grid, 128, sm, st>>>(p); }
+  { const int sm = 4 * 28 * 32 * (int)sizeof(uint4); if (sm > 48 * 1024) { e = cudaFuncSetAttribute(vit2_kernel<28, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(vit2)"); } vit2_kernel<28, true><<<grid, 128, sm, st>>>(p); }
+  { const int sm = 4 * 32 * 32 * (int)sizeof(uint4); if (sm > 48 * 1024) { e = cudaFuncSetAttribute(vit2_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(vit2)"); } vit2_kernel<32, true><<<grid, 128, sm, st>>>(p); }
   e = cudaGetLastError();
   return e == cudaSuccess ? CKM_OK : cuda_fail(e, "vit2_kernel launch");
 }

@@ -173,7 +173,7 @@ int models_build_device(ckm_models &db) {
     s.scale_b = m.scale_b; s.scale_w = m.scale_w;
     for (int z = 0; z < 6; ++z) s.evparam[z] = m.evparam[z];
     s.ddbound_w = m.ddbound_w;
-    s.vq = (m.M <= 64) ? 2 : (m.M <= 128) ? 4 : (m.M <= 256) ? 8 : (m.M <= 512) ? 16 : (m.M <= 1024) ? 32 : 0;
+    s.vq = (m.M <= 64) ? 2 : (m.M <= 128) ? 4 : (m.M <= 192) ? 6 : (m.M <= 256) ? 8 : (m.M <= 384) ? 12 : (m.M <= 512) ? 16 : (m.M <= 640) ? 20 : (m.M <= 768) ? 24 : (m.M <= 896) ? 28 : (m.M <= 1024) ? 32 : 0;
     s.blk_off = blk_units;
     blk_units += s.vq;
     db.maxM = std::max(db.maxM, m.M);

@@ -12,15 +12,30 @@ using namespace ckm;
 
 namespace ckm {
 
-// ---- device buffer with RAII ----
+// ---- device buffers come from the engine's grow-only cache: no cudaMalloc/cudaFree in the steady state ----
+static ckm_engine *g_pool_engine = nullptr;
+static int g_pool_next = 0;
+struct PoolScope {           // every search starts handing out slots from 0 again
+  explicit PoolScope(ckm_engine *e) { g_pool_engine = e; g_pool_next = 0; }
+  ~PoolScope() { g_pool_engine = nullptr; }
+};
 struct DevBuf {
-  void *p = nullptr; size_t bytes = 0;
-  ~DevBuf() { if (p) cudaFree(p); }
+  void *p = nullptr; size_t bytes = 0; int slot = -1;
   int alloc(size_t n) {
-    if (p) { cudaFree(p); p = nullptr; }
+    ckm_engine *e = g_pool_engine;
+    if (e == nullptr) { set_error("internal: workspace requested outside a search"); return CKM_EINVAL; }
+    if (slot < 0) { slot = g_pool_next++; if ((size_t)slot >= e->pool.size()) e->pool.resize(slot + 1, std::make_pair((void *)nullptr, (size_t)0)); }
     bytes = std::max<size_t>(n, 256);
-    cudaError_t e = cudaMalloc(&p, bytes);
-    if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaMalloc(workspace)"); }
+    auto &ent = e->pool[slot];
+    if (ent.second < bytes) {
+      if (ent.first) cudaFree(ent.first);
+      ent.first = nullptr; ent.second = 0;
+      const size_t want = bytes + bytes / 4;
+      cudaError_t err = cudaMalloc(&ent.first, want);
+      if (err != cudaSuccess) { err = cudaMalloc(&ent.first, bytes); if (err != cudaSuccess) { ent.first = nullptr; p = nullptr; return cuda_fail(err, "cudaMalloc(workspace)"); } ent.second = bytes; }
+      else ent.second = want;
+    }
+    p = ent.first;
     return CKM_OK;
   }
   template <class T> T *as() { return reinterpret_cast<T *>(p); }
@@ -200,7 +215,7 @@ static int run_stage2(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
   if (p.use_blk) { if ((rc = launch_fwd2(p, nsm * 8, st))) return rc; }
   if ((rc = launch_fwd(p, nsm * 4, st))) return rc;
   CKM_CUDA(cudaEventRecord(e->ev[5], st));
-  e->stats.kernel_launches += 8 + (p.use_blk ? 5 : 0);
+  e->stats.kernel_launches += 3 + 10 + (p.use_blk ? 10 : 0);
   s2.fwd_list = s2.a.as<Candidate>();
   return CKM_OK;
 }
@@ -214,6 +229,7 @@ int ckm_filter_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_i
   if (!e || !m || !db || !filtersc_out || !vit_out || !fwd_out || !passed_out) { set_error("ckm_filter_scores: bad argument"); return CKM_EINVAL; }
   cudaSetDevice(e->device);
   if (model_idx == nullptr) nmodels = (int32_t)m->models.size();
+  PoolScope pool_scope(e);
   ActiveMasks am; std::vector<int32_t> slot;
   int rc = build_masks(m, db, model_idx, nmodels, nullptr, am, slot, e->stream);
   if (rc) return rc;
@@ -264,7 +280,7 @@ int run_ensembles(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, Domde
                   const std::vector<Region> &regs, const std::vector<int> &multi_idx, std::vector<std::vector<Envelope>> &out);
 
 static bool use_blocked_kernels() { const char *v = std::getenv("CKM_BLK"); return !(v != nullptr && v[0] == '0'); }
-static int vq_of(int M) { return (M <= 64) ? 2 : (M <= 128) ? 4 : (M <= 256) ? 8 : (M <= 512) ? 16 : (M <= 1024) ? 32 : 0; }
+static int vq_of(int M) { return (M <= 64) ? 2 : (M <= 128) ? 4 : (M <= 192) ? 6 : (M <= 256) ? 8 : (M <= 384) ? 12 : (M <= 512) ? 16 : (M <= 640) ? 20 : (M <= 768) ? 24 : (M <= 896) ? 28 : (M <= 1024) ? 32 : 0; }
 
 static std::vector<float> &logsum_table() {
   static std::vector<float> t;
@@ -282,6 +298,7 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
   *hits_out = nullptr; *nhits_out = 0;
   const int ndb = (int)m->models.size();
   if (model_idx == nullptr && bin_model_offsets == nullptr) nmodels = ndb;
+  PoolScope pool_scope(e);
   ActiveMasks am; std::vector<int32_t> slot;
   int rc = build_masks(m, db, model_idx, nmodels, bin_model_offsets, am, slot, st);
   if (rc) return rc;
@@ -318,8 +335,6 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
   std::vector<Candidate> fl((size_t)npairs);
   if (npairs) CKM_CUDA(cudaMemcpy(fl.data(), s2.fwd_list, sizeof(Candidate) * fl.size(), cudaMemcpyDeviceToHost));
   std::sort(fl.begin(), fl.end(), [](const Candidate &a, const Candidate &b) { return a.seq != b.seq ? a.seq < b.seq : a.model < b.model; });
-  // free the big cascade buffers before the domain stage
-  s1.cand.alloc(0); s1.pass.alloc(0); s2.b.alloc(0);
 
   std::vector<PairWork> pairs((size_t)npairs);
   int64_t rows = 0;
@@ -352,7 +367,7 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
     p.logsum_tbl = dtbl.as<float>();
     p.row_elems = ((m->maxM + 31) / 32) * 32 + 64;
     p.tfb = m->d_tfb; p.rfb = m->d_rfb; p.use_blk = use_blocked_kernels() ? 1 : 0;
-    if (p.use_blk) { if ((rc = launch_regions2(p, std::min(nsm * 8, (npairs + 3) / 4), st))) return rc; e->stats.kernel_launches += 5; }
+    if (p.use_blk) { if ((rc = launch_regions2(p, std::min(nsm * 8, (npairs + 3) / 4), st))) return rc; e->stats.kernel_launches += 10; }
     if ((rc = launch_regions(p, std::min(nsm * 4, (npairs + FWD_WARPS - 1) / FWD_WARPS), st))) return rc;
     e->stats.kernel_launches++;
     int32_t nreg = 0;
@@ -394,7 +409,10 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
       }
       size_t free_b = 0, total_b = 0;
       cudaMemGetInfo(&free_b, &total_b);
-      const int64_t budget = std::max<int64_t>((int64_t)(free_b / 2 / sizeof(float)), *std::max_element(need.begin(), need.end()));
+      // fixed scratch budget (the cached pool is reused by every later search): 1/6 of the device, at most 24 GiB
+      (void)free_b;
+      int64_t budget = (int64_t)std::min<size_t>(total_b / 6, (size_t)24 << 30) / (int64_t)sizeof(float);
+      budget = std::max<int64_t>(budget, *std::max_element(need.begin(), need.end()));
       if ((rc = denvs.alloc(sizeof(Envelope) * envs.size())) || (rc = ddoms.alloc(sizeof(DomainOut) * envs.size())) || (rc = dhits.alloc(sizeof(HitOut) * pairs.size()))) return rc;
       CKM_CUDA(cudaMemcpyAsync(dpairs.p, pairs.data(), sizeof(PairWork) * pairs.size(), cudaMemcpyHostToDevice, st));
       size_t w0 = 0;
@@ -405,7 +423,7 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
         if (tot > cur_alloc) { if ((rc = dscratch.alloc(sizeof(float) * (size_t)tot))) return rc; cur_alloc = tot; }
         CKM_CUDA(cudaMemcpyAsync(denvs.as<Envelope>() + w0, envs.data() + w0, sizeof(Envelope) * (w1 - w0), cudaMemcpyHostToDevice, st));
         p.envs = denvs.as<Envelope>(); p.env_begin = (int32_t)w0; p.env_end = (int32_t)w1; p.scratch = dscratch.as<float>(); p.doms = ddoms.as<DomainOut>();
-        if (p.use_blk) { if ((rc = launch_envelopes2(p, std::min<int>(nsm * 8, (int)((w1 - w0 + 3) / 4)), st))) return rc; e->stats.kernel_launches += 5; }
+        if (p.use_blk) { if ((rc = launch_envelopes2(p, std::min<int>(nsm * 8, (int)((w1 - w0 + 3) / 4)), st))) return rc; e->stats.kernel_launches += 10; }
         if ((rc = launch_envelopes(p, std::min<int>(nsm * 4, (int)((w1 - w0 + FWD_WARPS - 1) / FWD_WARPS)), st))) return rc;
         e->stats.kernel_launches++;
         CKM_CUDA(cudaStreamSynchronize(st));
@@ -549,6 +567,7 @@ int ckm_msv_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_idx,
   if (!e || !m || !db || !xj_out) { set_error("ckm_msv_scores: bad argument"); return CKM_EINVAL; }
   cudaSetDevice(e->device);
   if (model_idx == nullptr) nmodels = (int32_t)m->models.size();
+  PoolScope pool_scope(e);
   ActiveMasks am; std::vector<int32_t> slot;
   int rc = build_masks(m, db, model_idx, nmodels, nullptr, am, slot, e->stream);
   if (rc) return rc;

@@ -20,9 +20,11 @@ def compare(rows, hits, tol_bits=2e-3):
         # null2-corrected scores go through the table-driven logsum (1/1000-nat bins, as in the reference pipeline): an
         # fp32 last-bit difference in its argument can move one bin = up to 7e-4 bits; allow 2e-3 bits + 1e-5 relative.
         # (The uncorrected Forward scores themselves are held to 1e-3 bits in test_filters_gpu.py; measured 2e-5.)
+        # the bias terms are fp32 sums of ~L per-residue log ratios (relative error ~1e-4 for L in the thousands) and enter the scores
+        slack = tol_bits + 1e-5 * abs(float(r['full_score'])) + 1e-4 * abs(float(r['full_bias']))
         for a, b in ((r['full_score'], h['full_score']), (r['dom_score'], h['dom_score']), (r['full_bias'], h['full_bias']), (r['dom_bias'], h['dom_bias'])):
             worst = max(worst, abs(float(a) - float(b)))
-            assert abs(float(a) - float(b)) < tol_bits + 1e-5 * abs(float(a)), (r, h)
+            assert abs(float(a) - float(b)) < slack, (r, h)
         assert abs(float(r['acc']) - float(h['acc'])) < 1e-3
         for a, b in ((r['full_E'], h['full_evalue']), (r['c_E'], h['c_evalue']), (r['i_E'], h['i_evalue'])):
             assert abs(np.log(max(a, 1e-300)) - np.log(max(float(b), 1e-300))) < 2e-3, (a, b)
