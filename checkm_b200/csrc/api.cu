@@ -41,6 +41,9 @@ int ckm_init(int device, ckm_engine **out) {
   }
   CKM_CUDA(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
   for (auto &ev : eng->ev) CKM_CUDA(cudaEventCreate(&ev));
+  for (auto &s : eng->cls) CKM_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  for (auto &ev : eng->cls_ev) CKM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CKM_CUDA(cudaEventCreateWithFlags(&eng->fan_ev, cudaEventDisableTiming));
   CKM_CUDA(cudaMalloc((void **)&eng->d_counters, 64 * sizeof(int32_t) + 64));
   std::memset(&eng->stats, 0, sizeof(eng->stats));
   *out = eng;
@@ -52,6 +55,9 @@ void ckm_destroy(ckm_engine *e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   for (auto &ev : e->ev) cudaEventDestroy(ev);
+  for (auto &s : e->cls) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+  for (auto &ev : e->cls_ev) cudaEventDestroy(ev);
+  cudaEventDestroy(e->fan_ev);
   cudaFree(e->d_counters);
   cudaFree(e->d_scratch);
   for (auto &ent : e->pool) cudaFree(ent.first);

@@ -133,6 +133,10 @@ struct ckm_engine {
   cudaDeviceProp prop;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[16];
+  // one stream per lane-block class (+1 for the unblocked kernels): the per-class launches of a stage run concurrently
+  static constexpr int NCLS = 11;
+  cudaStream_t cls[NCLS];
+  cudaEvent_t cls_ev[NCLS], fan_ev;
   ckm_stats stats;
   // grow-only device buffer cache: slot -> (pointer, bytes); search/reduce workspaces are reused across calls
   std::vector<std::pair<void *, size_t>> pool;

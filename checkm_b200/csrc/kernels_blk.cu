@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(BLK_WARPS * 32) regions2_kernel(DomdefParams p
   extern __shared__ __align__(16) uint8_t bsm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 *tsm = reinterpret_cast<float4 *>(bsm) + (size_t)warp * Q * 32 * 2;
-  for (int pi = blockIdx.x * BLK_WARPS + warp; pi < p.npairs; pi += gridDim.x * BLK_WARPS) {
+  for (int idx = p.pair_begin + blockIdx.x * BLK_WARPS + warp; idx < p.pair_end; idx += gridDim.x * BLK_WARPS) {
+    const int pi = p.pair_order[idx];
     const PairWork pw = p.pairs[pi];
     const ModelScalars ms = p.ms[pw.model];
     if (ms.vq != Q) continue;
@@ -84,7 +85,8 @@ __global__ void __launch_bounds__(BLK_WARPS * 32) envelope2_kernel(DomdefParams 
   float4 *tsm = reinterpret_cast<float4 *>(bsm) + (size_t)warp * Q * 32 * 2;
   float *null2 = reinterpret_cast<float *>(bsm + (TSMEM ? BLK_WARPS * blk_tsm_bytes<Q>() : 0)) + warp * 32;
   constexpr int QW = Q * 32;
-  for (int ei = p.env_begin + blockIdx.x * BLK_WARPS + warp; ei < p.env_end; ei += gridDim.x * BLK_WARPS) {
+  for (int idx = p.env_begin + blockIdx.x * BLK_WARPS + warp; idx < p.env_end; idx += gridDim.x * BLK_WARPS) {
+    const int ei = p.env_order[idx];
     const Envelope env = p.envs[ei];
     const PairWork pw = p.pairs[env.pair];
     const ModelScalars ms = p.ms[pw.model];
@@ -351,48 +353,26 @@ static int launch_one(KF kern, const P &p, int grid, size_t extra, cudaStream_t 
   return e == cudaSuccess ? CKM_OK : cuda_fail(e, what);
 }
 
-int launch_fwd2(const FilterParams &p, int grid, cudaStream_t st) {
-  int rc;
-  if ((rc = launch_one<2, false>(fwd2_kernel<2, false>, p, grid, 0, st, "fwd2_kernel<2>"))) return rc;
-  if ((rc = launch_one<4, false>(fwd2_kernel<4, false>, p, grid, 0, st, "fwd2_kernel<4>"))) return rc;
-  if ((rc = launch_one<6, false>(fwd2_kernel<6, false>, p, grid, 0, st, "fwd2_kernel<6>"))) return rc;
-  if ((rc = launch_one<8, false>(fwd2_kernel<8, false>, p, grid, 0, st, "fwd2_kernel<8>"))) return rc;
-  if ((rc = launch_one<12, true>(fwd2_kernel<12, true>, p, grid, 0, st, "fwd2_kernel<12>"))) return rc;
-  if ((rc = launch_one<16, true>(fwd2_kernel<16, true>, p, grid, 0, st, "fwd2_kernel<16>"))) return rc;
-  if ((rc = launch_one<20, true>(fwd2_kernel<20, true>, p, grid, 0, st, "fwd2_kernel<20>"))) return rc;
-  if ((rc = launch_one<24, true>(fwd2_kernel<24, true>, p, grid, 0, st, "fwd2_kernel<24>"))) return rc;
-  if ((rc = launch_one<28, true>(fwd2_kernel<28, true>, p, grid, 0, st, "fwd2_kernel<28>"))) return rc;
-  if ((rc = launch_one<32, true>(fwd2_kernel<32, true>, p, grid, 0, st, "fwd2_kernel<32>"))) return rc;
-  return CKM_OK;
-}
-int launch_regions2(const DomdefParams &p, int grid, cudaStream_t st) {
-  int rc;
-  if ((rc = launch_one<2, false>(regions2_kernel<2, false>, p, grid, 0, st, "regions2_kernel<2>"))) return rc;
-  if ((rc = launch_one<4, false>(regions2_kernel<4, false>, p, grid, 0, st, "regions2_kernel<4>"))) return rc;
-  if ((rc = launch_one<6, false>(regions2_kernel<6, false>, p, grid, 0, st, "regions2_kernel<6>"))) return rc;
-  if ((rc = launch_one<8, false>(regions2_kernel<8, false>, p, grid, 0, st, "regions2_kernel<8>"))) return rc;
-  if ((rc = launch_one<12, true>(regions2_kernel<12, true>, p, grid, 0, st, "regions2_kernel<12>"))) return rc;
-  if ((rc = launch_one<16, true>(regions2_kernel<16, true>, p, grid, 0, st, "regions2_kernel<16>"))) return rc;
-  if ((rc = launch_one<20, true>(regions2_kernel<20, true>, p, grid, 0, st, "regions2_kernel<20>"))) return rc;
-  if ((rc = launch_one<24, true>(regions2_kernel<24, true>, p, grid, 0, st, "regions2_kernel<24>"))) return rc;
-  if ((rc = launch_one<28, true>(regions2_kernel<28, true>, p, grid, 0, st, "regions2_kernel<28>"))) return rc;
-  if ((rc = launch_one<32, true>(regions2_kernel<32, true>, p, grid, 0, st, "regions2_kernel<32>"))) return rc;
-  return CKM_OK;
-}
-int launch_envelopes2(const DomdefParams &p, int grid, cudaStream_t st) {
-  int rc;
+#define CKM_CLASS_SWITCH(KERN, EXTRA, WHAT)                                                              \
+  switch (cls) {                                                                                        \
+    case 0: return launch_one<2, false>(KERN<2, false>, p, grid, EXTRA, st, WHAT);                      \
+    case 1: return launch_one<4, false>(KERN<4, false>, p, grid, EXTRA, st, WHAT);                      \
+    case 2: return launch_one<6, false>(KERN<6, false>, p, grid, EXTRA, st, WHAT);                      \
+    case 3: return launch_one<8, false>(KERN<8, false>, p, grid, EXTRA, st, WHAT);                      \
+    case 4: return launch_one<12, true>(KERN<12, true>, p, grid, EXTRA, st, WHAT);                      \
+    case 5: return launch_one<16, true>(KERN<16, true>, p, grid, EXTRA, st, WHAT);                      \
+    case 6: return launch_one<20, true>(KERN<20, true>, p, grid, EXTRA, st, WHAT);                      \
+    case 7: return launch_one<24, true>(KERN<24, true>, p, grid, EXTRA, st, WHAT);                      \
+    case 8: return launch_one<28, true>(KERN<28, true>, p, grid, EXTRA, st, WHAT);                      \
+    case 9: return launch_one<32, true>(KERN<32, true>, p, grid, EXTRA, st, WHAT);                      \
+  }                                                                                                     \
+  set_error(WHAT ": bad class"); return CKM_EINVAL;
+
+int launch_fwd2(const FilterParams &p, int cls, int grid, cudaStream_t st) { CKM_CLASS_SWITCH(fwd2_kernel, 0, "fwd2_kernel") }
+int launch_regions2(const DomdefParams &p, int cls, int grid, cudaStream_t st) { CKM_CLASS_SWITCH(regions2_kernel, 0, "regions2_kernel") }
+int launch_envelopes2(const DomdefParams &p, int cls, int grid, cudaStream_t st) {
   const size_t extra = BLK_WARPS * 32 * sizeof(float);
-  if ((rc = launch_one<2, false>(envelope2_kernel<2, false>, p, grid, extra, st, "envelope2_kernel<2>"))) return rc;
-  if ((rc = launch_one<4, false>(envelope2_kernel<4, false>, p, grid, extra, st, "envelope2_kernel<4>"))) return rc;
-  if ((rc = launch_one<6, false>(envelope2_kernel<6, false>, p, grid, extra, st, "envelope2_kernel<6>"))) return rc;
-  if ((rc = launch_one<8, false>(envelope2_kernel<8, false>, p, grid, extra, st, "envelope2_kernel<8>"))) return rc;
-  if ((rc = launch_one<12, true>(envelope2_kernel<12, true>, p, grid, extra, st, "envelope2_kernel<12>"))) return rc;
-  if ((rc = launch_one<16, true>(envelope2_kernel<16, true>, p, grid, extra, st, "envelope2_kernel<16>"))) return rc;
-  if ((rc = launch_one<20, true>(envelope2_kernel<20, true>, p, grid, extra, st, "envelope2_kernel<20>"))) return rc;
-  if ((rc = launch_one<24, true>(envelope2_kernel<24, true>, p, grid, extra, st, "envelope2_kernel<24>"))) return rc;
-  if ((rc = launch_one<28, true>(envelope2_kernel<28, true>, p, grid, extra, st, "envelope2_kernel<28>"))) return rc;
-  if ((rc = launch_one<32, true>(envelope2_kernel<32, true>, p, grid, extra, st, "envelope2_kernel<32>"))) return rc;
-  return CKM_OK;
+  CKM_CLASS_SWITCH(envelope2_kernel, extra, "envelope2_kernel")
 }
 
 }  // namespace ckm

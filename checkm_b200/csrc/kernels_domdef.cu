@@ -26,11 +26,11 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) regions_kernel(DomdefParams p)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float *rowM = reinterpret_cast<float *>(smem) + (size_t)warp * 3 * p.row_elems;
   float *rowI = rowM + p.row_elems, *rowD = rowI + p.row_elems;
-  for (int pi = blockIdx.x * FWD_WARPS + warp; pi < p.npairs; pi += gridDim.x * FWD_WARPS) {
+  for (int idx = p.pair_begin + blockIdx.x * FWD_WARPS + warp; idx < p.pair_end; idx += gridDim.x * FWD_WARPS) {
+    const int pi = p.pair_order[idx];                 // the host lists here only pairs without a lane-block class
     const PairWork pw = p.pairs[pi];
     const int L = pw.L;
     const ModelScalars ms = p.ms[pw.model];
-    if (p.use_blk && ms.vq != 0) continue;            // handled by regions2_kernel<Q>
     const FwdModel fm = make_fwd_model(p, ms);
     const uint8_t *res = p.res + p.off[pw.seq];
     const Specials sp = make_specials(L, true);
@@ -54,11 +54,11 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) envelope_kernel(DomdefParams p
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float *rowM = reinterpret_cast<float *>(smem) + (size_t)warp * 3 * p.row_elems;
   float *rowI = rowM + p.row_elems, *rowD = rowI + p.row_elems;
-  for (int ei = p.env_begin + blockIdx.x * FWD_WARPS + warp; ei < p.env_end; ei += gridDim.x * FWD_WARPS) {
+  for (int idx = p.env_begin + blockIdx.x * FWD_WARPS + warp; idx < p.env_end; idx += gridDim.x * FWD_WARPS) {
+    const int ei = p.env_order[idx];                  // the host lists here only envelopes without a lane-block class
     const Envelope env = p.envs[ei];
     const PairWork pw = p.pairs[env.pair];
     const ModelScalars ms = p.ms[pw.model];
-    if (p.use_blk && ms.vq != 0) continue;            // handled by envelope2_kernel<Q>
     const FwdModel fm = make_fwd_model(p, ms);
     const int M = fm.M, Mpad = fm.Mpad, Ld = env.j - env.i + 1, nchunk = (M + 31) >> 5;
     const uint8_t *res = p.res + p.off[pw.seq] + (env.i - 1);

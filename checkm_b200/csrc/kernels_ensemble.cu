@@ -8,6 +8,7 @@
 #include "device_utils.cuh"
 #include "stages.hpp"
 #include "fwdback.cuh"
+#include "pool.hpp"
 
 namespace ckm {
 
@@ -96,6 +97,9 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) ensemble_kernel(EnsembleParams
     for (int pos = lane; pos <= Lr; pos += 32) acc[pos] = 0.0f;
     __syncwarp();
     Lcg rng; rng.x = mix3(42u, 87654321u, 12345678u); if (rng.x == 0) rng.x = 42;
+    // generator jump for the run fast paths: lane l sees draw number l+1 from the current state, x -> jA x + jC
+    uint32_t jA = 1u, jC = 0u;
+    for (int z = 0; z <= lane; ++z) { jC = jC * 69069u + 1u; jA *= 69069u; }
     int nsp = 0;
     float *cm = rowM, *ci = rowI, *null2 = rowD;
     for (int t = 0; t < NSAMPLES; ++t) {
@@ -110,6 +114,68 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) ensemble_kernel(EnsembleParams
       while (s0 != ST_S) {
         if (++guard > gmax) { failed = true; break; }
         float pth[4];
+        // ---- run fast paths.  A walk spends most of its steps in M->M diagonals and in C/J self loops; each step
+        // costs one draw and depends only on the cell it stands on, so lane l evaluates the step l places ahead
+        // (its cell's path odds, normalised and compared with draw l+1 exactly as the single-step code does) and the
+        // warp takes the whole leading run in one memory round trip.  Anything unusual falls to the single-step code. ----
+        if (s0 == ST_M || s0 == ST_C || s0 == ST_J) {
+          const bool isM = (s0 == ST_M);
+          const int ii = i - lane, kk = k - lane;
+          const bool valid = isM ? (ii >= 1 && kk >= 1) : (ii >= 0);
+          float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+          if (valid) {
+            if (isM) {
+              const float *dpp = F + (int64_t)(ii - 1) * 3 * Mpad;
+              const float4 t0 = __ldg(fm.tfv + 2 * kk);
+              p0 = __fmul_rn(xf[(int64_t)(ii - 1) * X_NX + X_B], t0.x);
+              p1 = __fmul_rn(dpp[kk - 1], t0.y);
+              p2 = __fmul_rn(dpp[2 * Mpad + kk - 1], t0.z);
+              p3 = __fmul_rn(dpp[Mpad + kk - 1], t0.w);
+            } else {
+              const int XS = (s0 == ST_C) ? X_C : X_J;
+              const float tmv = (s0 == ST_C) ? sp.emove : sp.eloop;
+              p0 = (ii > 0) ? __fmul_rn(xf[(int64_t)(ii - 1) * X_NX + XS], sp.nloop) : 0.0f;
+              p1 = __fmul_rn(__fmul_rn(xf[(int64_t)ii * X_NX + X_E], tmv), xf[(int64_t)ii * X_NX + X_SCALE]);
+            }
+          }
+          const int np = isM ? 4 : 2;
+          float sum = __fadd_rn(__fadd_rn(0.0f, p0), p1);
+          if (isM) sum = __fadd_rn(__fadd_rn(sum, p2), p3);
+          if (sum != 0.0f) { const float sc = (float)(1.0 / (double)sum); p0 = __fmul_rn(p0, sc); p1 = __fmul_rn(p1, sc); p2 = __fmul_rn(p2, sc); p3 = __fmul_rn(p3, sc); }
+          else { const float u = __fdiv_rn(1.0f, (float)np); p0 = u; p1 = u; p2 = u; p3 = u; }
+          const uint32_t xl = jA * rng.x + jC;
+          const float roll = (float)((double)xl / 4294967296.0);
+          const float c0 = __fadd_rn(0.0f, p0), c1 = __fadd_rn(c0, p1), c2 = __fadd_rn(c1, p2), c3 = __fadd_rn(c2, p3);
+          int choice = -1;
+          if (roll < c0) choice = 0; else if (roll < c1) choice = 1; else if (isM && roll < c2) choice = 2; else if (isM && roll < c3) choice = 3;
+          const bool okl = valid && choice >= 0;
+          const int stay = isM ? 1 : 0;                   // the choice that continues the run
+          const unsigned cont = __ballot_sync(0xffffffffu, okl && choice == stay);
+          const int nlead = (cont == 0xffffffffu) ? 32 : (__ffs(~cont) - 1);
+          const int okf = (nlead < 32) ? __shfl_sync(0xffffffffu, (int)okl, nlead & 31) : 0;
+          const int cf = __shfl_sync(0xffffffffu, choice, nlead & 31);
+          const int nproc = nlead + (okf ? 1 : 0);
+          if (nproc > 0) {
+            guard += nproc - 1;
+            if (nlead > 0) {
+              if (isM) {
+                if (in_dom) {
+                  if (sqto == 0) sqto = i - 1;
+                  if (hmmto == 0) hmmto = k - 1;
+                  sqfrom = i - nlead; hmmfrom = k - nlead; ldom += nlead;
+                  if (lane < nlead) cm[k - lane - 1] += 1.0f;
+                }
+                k -= nlead;
+              }
+              i -= nlead;
+            }
+            rng.x = __shfl_sync(0xffffffffu, xl, nproc - 1);
+            if (!okf) continue;                           // still inside the run: s0 unchanged
+            if (isM) { s1 = (cf == 0) ? ST_B : (cf == 2) ? ST_I : ST_D; k--; i--; }
+            else s1 = ST_E;
+            goto step_done;
+          }
+        }
         if (s0 == ST_M) {
           const float *dpp = F + (int64_t)(i - 1) * 3 * Mpad;
           const float4 t0 = __ldg(fm.tfv + 2 * k);
@@ -133,7 +199,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) ensemble_kernel(EnsembleParams
           pth[1] = __fmul_rn(dpp[2 * Mpad + k], t1.z);
           s1 = fchoose(rng, pth, 2) == 0 ? ST_M : ST_I; i--;
         } else if (s0 == ST_N) {
-          s1 = (i == 0) ? ST_S : ST_N;
+          i = 0; s1 = ST_S;                               // N loops back to the start without draws or bookkeeping
         } else if (s0 == ST_C) {
           pth[0] = (i > 0) ? __fmul_rn(xf[(int64_t)(i - 1) * X_NX + X_C], sp.nloop) : 0.0f;
           pth[1] = __fmul_rn(__fmul_rn(xf[(int64_t)i * X_NX + X_E], sp.emove), xf[(int64_t)i * X_NX + X_SCALE]);
@@ -187,6 +253,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) ensemble_kernel(EnsembleParams
           for (int kk = lane; kk <= M; kk += 32) { cm[kk] = 0.0f; ci[kk] = 0.0f; }
           __syncwarp();
         } else { failed = true; break; }
+      step_done:
         // bookkeeping for the state just entered (coordinates k, i are those of s1)
         if (in_dom) {
           if (s1 == ST_M) {
@@ -333,15 +400,12 @@ int run_ensembles(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, Domde
     tot += (Lr + 1) * 3 * Mpad + (Lr + 1) * X_NX + 2 * (Lr + 1) + (int64_t)SPCAP * 8 + std::max(Lr, M) + 2 + 256 + 64;
     tot = (tot + 63) / 64 * 64;
   }
-  void *d_regs = nullptr, *d_idx = nullptr, *d_off = nullptr, *d_scr = nullptr, *d_env = nullptr, *d_cnt = nullptr;
-  auto cleanup = [&]() { cudaFree(d_regs); cudaFree(d_idx); cudaFree(d_off); cudaFree(d_scr); cudaFree(d_env); cudaFree(d_cnt); };
-#define ENS_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #call); } } while (0)
-  ENS_CUDA(cudaMalloc(&d_regs, sizeof(Region) * regs.size()));
-  ENS_CUDA(cudaMalloc(&d_idx, sizeof(int32_t) * nm));
-  ENS_CUDA(cudaMalloc(&d_off, sizeof(int64_t) * nm));
-  ENS_CUDA(cudaMalloc(&d_scr, sizeof(float) * (size_t)tot));
-  ENS_CUDA(cudaMalloc(&d_env, sizeof(Envelope) * (size_t)nm * MAXENV));
-  ENS_CUDA(cudaMalloc(&d_cnt, sizeof(int32_t) * nm));
+  DevBuf b_regs, b_idx, b_off, b_scr, b_env, b_cnt;       // workspaces from the engine's cache (the caller holds the PoolScope)
+  int rc;
+  if ((rc = b_regs.alloc(sizeof(Region) * regs.size())) || (rc = b_idx.alloc(sizeof(int32_t) * nm)) || (rc = b_off.alloc(sizeof(int64_t) * nm)) ||
+      (rc = b_scr.alloc(sizeof(float) * (size_t)tot)) || (rc = b_env.alloc(sizeof(Envelope) * (size_t)nm * MAXENV)) || (rc = b_cnt.alloc(sizeof(int32_t) * nm))) return rc;
+  void *d_regs = b_regs.p, *d_idx = b_idx.p, *d_off = b_off.p, *d_scr = b_scr.p, *d_env = b_env.p, *d_cnt = b_cnt.p;
+#define ENS_CUDA(call) CKM_CUDA(call)
   ENS_CUDA(cudaMemcpyAsync(d_regs, regs.data(), sizeof(Region) * regs.size(), cudaMemcpyHostToDevice, st));
   ENS_CUDA(cudaMemcpyAsync(d_idx, multi_idx.data(), sizeof(int32_t) * nm, cudaMemcpyHostToDevice, st));
   ENS_CUDA(cudaMemcpyAsync(d_off, off.data(), sizeof(int64_t) * nm, cudaMemcpyHostToDevice, st));
@@ -362,7 +426,6 @@ int run_ensembles(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, Domde
   ENS_CUDA(cudaStreamSynchronize(st));
   for (int i = 0; i < nm; ++i)
     for (int c = 0; c < cnt[i]; ++c) out[i].push_back(envs[(size_t)i * MAXENV + c]);
-  cleanup();
   return CKM_OK;
 }
 

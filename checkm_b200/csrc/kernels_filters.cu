@@ -336,20 +336,31 @@ int launch_bias(const FilterParams &p, int grid, cudaStream_t st) {
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? CKM_OK : cuda_fail(e, "bias_kernel launch");
 }
-int launch_vit2(const FilterParams &p, int grid, cudaStream_t st) {
-  cudaError_t e;
-  vit2_kernel<2, false><<<grid, 128, 0, st>>>(p);
-  vit2_kernel<4, false><<<grid, 128, 0, st>>>(p);
-  vit2_kernel<6, false><<<grid, 128, 0, st>>>(p);
-  vit2_kernel<8, false><<<grid, 128, 0, st>>>(p);
-  { const int sm = 4 * 12 * 32 * (int)sizeof(uint4); if (sm > 48 * 1024) { e = cudaFuncSetAttribute(vit2_kernel<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(vit2)"); } vit2_kernel<12, true><<<grid, 128, sm, st>>>(p); }
-  { const int sm = 4 * 16 * 32 * (int)sizeof(uint4); if (sm > 48 * 1024) { e = cudaFuncSetAttribute(vit2_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(vit2)"); } vit2_kernel<16, true><<<grid, 128, sm, st>>>(p); }
-  { const int sm = 4 * 20 * 32 * (int)sizeof(uint4); if (sm > 48 * 1024) { e = cudaFuncSetAttribute(vit2_kernel<20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(vit2)"); } vit2_kernel<20, true><<<grid, 128, sm, st>>>(p); }
-  { const int sm = 4 * 24 * 32 * (int)sizeof(uint4); if (sm > 48 * 1024) { e = cudaFuncSetAttribute(vit2_kernel<24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(vit2)"); } vit2_kernel<24, true><<<grid, 128, sm, st>>>(p); }
-  { const int sm = 4 * 28 * 32 * (int)sizeof(uint4); if (sm > 48 * 1024) { e = cudaFuncSetAttribute(vit2_kernel<28, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(vit2)"); } vit2_kernel<28, true><<<grid, 128, sm, st>>>(p); }
-  { const int sm = 4 * 32 * 32 * (int)sizeof(uint4); if (sm > 48 * 1024) { e = cudaFuncSetAttribute(vit2_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(vit2)"); } vit2_kernel<32, true><<<grid, 128, sm, st>>>(p); }
-  e = cudaGetLastError();
+template <int Q, bool TSMEM>
+static int launch_vit2_q(const FilterParams &p, int grid, cudaStream_t st) {
+  const int sm = TSMEM ? 4 * Q * 32 * (int)sizeof(uint4) : 0;
+  if (sm > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(vit2_kernel<Q, TSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(vit2)");
+  }
+  vit2_kernel<Q, TSMEM><<<grid, 128, sm, st>>>(p);
+  cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? CKM_OK : cuda_fail(e, "vit2_kernel launch");
+}
+int launch_vit2(const FilterParams &p, int cls, int grid, cudaStream_t st) {
+  switch (cls) {
+    case 0: return launch_vit2_q<2, false>(p, grid, st);
+    case 1: return launch_vit2_q<4, false>(p, grid, st);
+    case 2: return launch_vit2_q<6, false>(p, grid, st);
+    case 3: return launch_vit2_q<8, false>(p, grid, st);
+    case 4: return launch_vit2_q<12, true>(p, grid, st);
+    case 5: return launch_vit2_q<16, true>(p, grid, st);
+    case 6: return launch_vit2_q<20, true>(p, grid, st);
+    case 7: return launch_vit2_q<24, true>(p, grid, st);
+    case 8: return launch_vit2_q<28, true>(p, grid, st);
+    case 9: return launch_vit2_q<32, true>(p, grid, st);
+  }
+  set_error("launch_vit2: bad class"); return CKM_EINVAL;
 }
 int launch_vit(const FilterParams &p, int grid, cudaStream_t st) {
   const size_t smem = (size_t)VIT_WARPS * 3 * p.row_elems * sizeof(int16_t);

@@ -7,41 +7,15 @@
 #include <vector>
 #include "engine.hpp"
 #include "stages.hpp"
+#include "pool.hpp"
 
 using namespace ckm;
 
 namespace ckm {
 
-// ---- device buffers come from the engine's grow-only cache: no cudaMalloc/cudaFree in the steady state ----
-static ckm_engine *g_pool_engine = nullptr;
-static int g_pool_next = 0;
-struct PoolScope {           // every search starts handing out slots from 0 again
-  explicit PoolScope(ckm_engine *e) { g_pool_engine = e; g_pool_next = 0; }
-  ~PoolScope() { g_pool_engine = nullptr; }
-};
-struct DevBuf {
-  void *p = nullptr; size_t bytes = 0; int slot = -1;
-  int alloc(size_t n) {
-    ckm_engine *e = g_pool_engine;
-    if (e == nullptr) { set_error("internal: workspace requested outside a search"); return CKM_EINVAL; }
-    if (slot < 0) { slot = g_pool_next++; if ((size_t)slot >= e->pool.size()) e->pool.resize(slot + 1, std::make_pair((void *)nullptr, (size_t)0)); }
-    bytes = std::max<size_t>(n, 256);
-    auto &ent = e->pool[slot];
-    if (ent.second < bytes) {
-      if (ent.first) cudaFree(ent.first);
-      ent.first = nullptr; ent.second = 0;
-      const size_t want = bytes + bytes / 4;
-      cudaError_t err = cudaMalloc(&ent.first, want);
-      if (err != cudaSuccess) { err = cudaMalloc(&ent.first, bytes); if (err != cudaSuccess) { ent.first = nullptr; p = nullptr; return cuda_fail(err, "cudaMalloc(workspace)"); } ent.second = bytes; }
-      else ent.second = want;
-    }
-    p = ent.first;
-    return CKM_OK;
-  }
-  template <class T> T *as() { return reinterpret_cast<T *>(p); }
-};
-
 static bool use_blocked_kernels();
+static int fan_out(ckm_engine *e);
+static int fan_in(ckm_engine *e);
 enum { CTR_UNIT4 = 0, CTR_UNIT8, CTR_UNIT16, CTR_UNIT32, CTR_CAND, CTR_MSV, CTR_BIAS, CTR_VIT, CTR_FWD, CTR_ENV, CTR_DOM, CTR_N = 32 };
 
 struct ActiveMasks {
@@ -206,16 +180,20 @@ static int run_stage2(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
   // viterbi: a -> b
   p.in = s2.a.as<Candidate>(); p.in_count = e->d_counters + CTR_BIAS; p.in_cap = s2.cap;
   p.out = s2.b.as<Candidate>(); p.out_count = e->d_counters + CTR_VIT; p.out_cap = s2.cap;
-  if ((rc = launch_vit2(p, nsm * 8, st))) return rc;      // models up to M = 512: lane-blocked register kernels
-  if ((rc = launch_vit(p, nsm * 4, st))) return rc;       // longer models: shared-memory rows
+  if ((rc = fan_out(e))) return rc;
+  for (int c = 0; c < N_BLK_CLASSES; ++c) if ((rc = launch_vit2(p, c, nsm * 8, e->cls[c]))) return rc;      // lane-blocked register kernels, one per class
+  if ((rc = launch_vit(p, nsm * 4, e->cls[N_BLK_CLASSES]))) return rc;                                      // models beyond the classes: shared-memory rows
+  if ((rc = fan_in(e))) return rc;
   CKM_CUDA(cudaEventRecord(e->ev[4], st));
   // forward: b -> a
   p.in = s2.b.as<Candidate>(); p.in_count = e->d_counters + CTR_VIT; p.in_cap = s2.cap;
   p.out = s2.a.as<Candidate>(); p.out_count = e->d_counters + CTR_FWD; p.out_cap = s2.cap;
-  if (p.use_blk) { if ((rc = launch_fwd2(p, nsm * 8, st))) return rc; }
-  if ((rc = launch_fwd(p, nsm * 4, st))) return rc;
+  if ((rc = fan_out(e))) return rc;
+  if (p.use_blk) { for (int c = 0; c < N_BLK_CLASSES; ++c) if ((rc = launch_fwd2(p, c, nsm * 8, e->cls[c]))) return rc; }
+  if ((rc = launch_fwd(p, nsm * 4, e->cls[N_BLK_CLASSES]))) return rc;
+  if ((rc = fan_in(e))) return rc;
   CKM_CUDA(cudaEventRecord(e->ev[5], st));
-  e->stats.kernel_launches += 3 + 10 + (p.use_blk ? 10 : 0);
+  e->stats.kernel_launches += 3 + N_BLK_CLASSES + (p.use_blk ? N_BLK_CLASSES : 0);
   s2.fwd_list = s2.a.as<Candidate>();
   return CKM_OK;
 }
@@ -282,6 +260,26 @@ int run_ensembles(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, Domde
 static bool use_blocked_kernels() { const char *v = std::getenv("CKM_BLK"); return !(v != nullptr && v[0] == '0'); }
 static int vq_of(int M) { return (M <= 64) ? 2 : (M <= 128) ? 4 : (M <= 192) ? 6 : (M <= 256) ? 8 : (M <= 384) ? 12 : (M <= 512) ? 16 : (M <= 640) ? 20 : (M <= 768) ? 24 : (M <= 896) ? 28 : (M <= 1024) ? 32 : 0; }
 
+static int cls_of(int M, bool use_blk) {      // class index: 0..9 lane-block classes, 10 = unblocked kernels
+  if (!use_blk) return N_BLK_CLASSES;
+  const int q = vq_of(M);
+  for (int c = 0; c < N_BLK_CLASSES; ++c) if (BLK_Q[c] == q) return c;
+  return N_BLK_CLASSES;
+}
+// the per-class launches of one stage go to the engine's class streams: fork after the main stream, join back into it
+static int fan_out(ckm_engine *e) {
+  CKM_CUDA(cudaEventRecord(e->fan_ev, e->stream));
+  for (auto &s : e->cls) CKM_CUDA(cudaStreamWaitEvent(s, e->fan_ev, 0));
+  return CKM_OK;
+}
+static int fan_in(ckm_engine *e) {
+  for (int c = 0; c < ckm_engine::NCLS; ++c) {
+    CKM_CUDA(cudaEventRecord(e->cls_ev[c], e->cls[c]));
+    CKM_CUDA(cudaStreamWaitEvent(e->stream, e->cls_ev[c], 0));
+  }
+  return CKM_OK;
+}
+
 static std::vector<float> &logsum_table() {
   static std::vector<float> t;
   if (t.empty()) { t.resize(16000); for (int i = 0; i < 16000; ++i) t[i] = (float)std::log(1.0 + std::exp((double)-i / 1000.0)); }
@@ -345,7 +343,7 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
     pw.row_off = rows; rows += pw.L + 1;
   }
   const int nsm = e->prop.multiProcessorCount;
-  DevBuf dpairs, dxf, dxb, dvec, dregions, denvs, ddoms, dhits, dscratch, dtbl;
+  DevBuf dpairs, dxf, dxb, dvec, dregions, denvs, ddoms, dhits, dscratch, dtbl, dporder, deorder;
   std::vector<DomainOut> doms; std::vector<HitOut> hout((size_t)npairs);
   std::vector<Envelope> envs;
   CKM_CUDA(cudaEventRecord(e->ev[6], st));
@@ -367,9 +365,31 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
     p.logsum_tbl = dtbl.as<float>();
     p.row_elems = ((m->maxM + 31) / 32) * 32 + 64;
     p.tfb = m->d_tfb; p.rfb = m->d_rfb; p.use_blk = use_blocked_kernels() ? 1 : 0;
-    if (p.use_blk) { if ((rc = launch_regions2(p, std::min(nsm * 8, (npairs + 3) / 4), st))) return rc; e->stats.kernel_launches += 10; }
-    if ((rc = launch_regions(p, std::min(nsm * 4, (npairs + FWD_WARPS - 1) / FWD_WARPS), st))) return rc;
-    e->stats.kernel_launches++;
+    {
+      // pairs grouped by class, longest target first inside a class; every class runs on its own stream
+      std::vector<int32_t> order((size_t)npairs);
+      std::vector<int8_t> pcls((size_t)npairs);
+      for (int i = 0; i < npairs; ++i) { order[i] = i; pcls[i] = (int8_t)cls_of(m->models[pairs[i].model].M, p.use_blk != 0); }
+      std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return pcls[a] != pcls[b] ? pcls[a] < pcls[b] : pairs[a].L > pairs[b].L; });
+      if ((rc = dporder.alloc(sizeof(int32_t) * order.size()))) return rc;
+      CKM_CUDA(cudaMemcpyAsync(dporder.p, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice, st));
+      p.pair_order = dporder.as<int32_t>();
+      if ((rc = fan_out(e))) return rc;
+      int b0 = 0;
+      while (b0 < npairs) {
+        int b1 = b0; const int c = pcls[order[b0]];
+        while (b1 < npairs && pcls[order[b1]] == c) ++b1;
+        p.pair_begin = b0; p.pair_end = b1;
+        const int cnt = b1 - b0;
+        if (c < N_BLK_CLASSES) rc = launch_regions2(p, c, std::min(nsm * 8, (cnt + 3) / 4), e->cls[c]);
+        else rc = launch_regions(p, std::min(nsm * 4, (cnt + FWD_WARPS - 1) / FWD_WARPS), e->cls[c]);
+        if (rc) return rc;
+        e->stats.kernel_launches++;
+        b0 = b1;
+      }
+      if ((rc = fan_in(e))) return rc;
+      CKM_CUDA(cudaStreamSynchronize(st));   // `order` is read by the copy above
+    }
     int32_t nreg = 0;
     CKM_CUDA(cudaMemcpyAsync(&nreg, e->d_counters + CTR_ENV, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CKM_CUDA(cudaStreamSynchronize(st));
@@ -409,23 +429,42 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
       }
       size_t free_b = 0, total_b = 0;
       cudaMemGetInfo(&free_b, &total_b);
-      // fixed scratch budget (the cached pool is reused by every later search): 1/6 of the device, at most 24 GiB
+      // fixed scratch budget (the cached pool is reused by every later search): 1/3 of the device, at most 56 GiB
       (void)free_b;
-      int64_t budget = (int64_t)std::min<size_t>(total_b / 6, (size_t)24 << 30) / (int64_t)sizeof(float);
+      int64_t budget = (int64_t)std::min<size_t>(total_b / 3, (size_t)56 << 30) / (int64_t)sizeof(float);
       budget = std::max<int64_t>(budget, *std::max_element(need.begin(), need.end()));
       if ((rc = denvs.alloc(sizeof(Envelope) * envs.size())) || (rc = ddoms.alloc(sizeof(DomainOut) * envs.size())) || (rc = dhits.alloc(sizeof(HitOut) * pairs.size()))) return rc;
       CKM_CUDA(cudaMemcpyAsync(dpairs.p, pairs.data(), sizeof(PairWork) * pairs.size(), cudaMemcpyHostToDevice, st));
+      std::vector<int8_t> ecls(envs.size());
+      for (size_t i = 0; i < envs.size(); ++i) ecls[i] = (int8_t)cls_of(m->models[pairs[envs[i].pair].model].M, p.use_blk != 0);
+      if ((rc = deorder.alloc(sizeof(int32_t) * envs.size()))) return rc;
+      std::vector<int32_t> eorder(envs.size());
       size_t w0 = 0;
       int64_t cur_alloc = 0;
       while (w0 < envs.size()) {
         size_t w1 = w0; int64_t tot = 0;
         while (w1 < envs.size() && (w1 == w0 || tot + need[w1] <= budget)) { envs[w1].scratch_off = tot; tot += need[w1]; ++w1; }
         if (tot > cur_alloc) { if ((rc = dscratch.alloc(sizeof(float) * (size_t)tot))) return rc; cur_alloc = tot; }
+        // this wave's envelopes grouped by class, largest first; one stream per class
+        for (size_t i = w0; i < w1; ++i) eorder[i] = (int32_t)i;
+        std::stable_sort(eorder.begin() + w0, eorder.begin() + w1, [&](int32_t a, int32_t b) { return ecls[a] != ecls[b] ? ecls[a] < ecls[b] : need[a] > need[b]; });
         CKM_CUDA(cudaMemcpyAsync(denvs.as<Envelope>() + w0, envs.data() + w0, sizeof(Envelope) * (w1 - w0), cudaMemcpyHostToDevice, st));
-        p.envs = denvs.as<Envelope>(); p.env_begin = (int32_t)w0; p.env_end = (int32_t)w1; p.scratch = dscratch.as<float>(); p.doms = ddoms.as<DomainOut>();
-        if (p.use_blk) { if ((rc = launch_envelopes2(p, std::min<int>(nsm * 8, (int)((w1 - w0 + 3) / 4)), st))) return rc; e->stats.kernel_launches += 10; }
-        if ((rc = launch_envelopes(p, std::min<int>(nsm * 4, (int)((w1 - w0 + FWD_WARPS - 1) / FWD_WARPS)), st))) return rc;
-        e->stats.kernel_launches++;
+        CKM_CUDA(cudaMemcpyAsync(deorder.as<int32_t>() + w0, eorder.data() + w0, sizeof(int32_t) * (w1 - w0), cudaMemcpyHostToDevice, st));
+        p.envs = denvs.as<Envelope>(); p.env_order = deorder.as<int32_t>(); p.scratch = dscratch.as<float>(); p.doms = ddoms.as<DomainOut>();
+        if ((rc = fan_out(e))) return rc;
+        size_t b0 = w0;
+        while (b0 < w1) {
+          size_t b1 = b0; const int c = ecls[eorder[b0]];
+          while (b1 < w1 && ecls[eorder[b1]] == c) ++b1;
+          p.env_begin = (int32_t)b0; p.env_end = (int32_t)b1;
+          const int cnt = (int)(b1 - b0);
+          if (c < N_BLK_CLASSES) rc = launch_envelopes2(p, c, std::min<int>(nsm * 8, (cnt + 3) / 4), e->cls[c]);
+          else rc = launch_envelopes(p, std::min<int>(nsm * 4, (cnt + FWD_WARPS - 1) / FWD_WARPS), e->cls[c]);
+          if (rc) return rc;
+          e->stats.kernel_launches++;
+          b0 = b1;
+        }
+        if ((rc = fan_in(e))) return rc;
         CKM_CUDA(cudaStreamSynchronize(st));
         w0 = w1;
       }

@@ -65,7 +65,10 @@ struct FilterParams {
 };
 int launch_bias(const FilterParams &p, int grid, cudaStream_t st);
 int launch_vit(const FilterParams &p, int grid, cudaStream_t st);
-int launch_vit2(const FilterParams &p, int grid, cudaStream_t st);
+// lane-block classes: class index c (0..9) keeps BLK_Q[c] model positions per lane; index 10 = the unblocked kernels
+constexpr int N_BLK_CLASSES = 10;
+constexpr int BLK_Q[N_BLK_CLASSES] = {2, 4, 6, 8, 12, 16, 20, 24, 28, 32};
+int launch_vit2(const FilterParams &p, int cls, int grid, cudaStream_t st);
 int launch_fwd(const FilterParams &p, int grid, cudaStream_t st);
 
 // ---- stage 5: domain definition ----
@@ -88,9 +91,10 @@ struct DomdefParams {
   const uint8_t *res; const int64_t *off; const float *nullsc;
   const ModelScalars *ms; const float *rfv; const float *tfv;
   const PairWork *pairs; int32_t npairs;
+  const int32_t *pair_order; int32_t pair_begin, pair_end;   // regions kernels walk pair_order[pair_begin..pair_end) (one class, longest first)
   float *xf, *xb, *btot, *etot, *mocc, *n2sc;      // per-pair arrays, indexed by row_off
   Region *regions; int32_t *region_count; int32_t region_cap;
-  const Envelope *envs; int32_t env_begin, env_end;
+  const Envelope *envs; const int32_t *env_order; int32_t env_begin, env_end;   // envelope kernels walk env_order[env_begin..env_end)
   float *scratch;
   DomainOut *doms; HitOut *hits;
   const float *logsum_tbl;
@@ -101,8 +105,8 @@ struct DomdefParams {
 int launch_regions(const DomdefParams &p, int grid, cudaStream_t st);
 int launch_envelopes(const DomdefParams &p, int grid, cudaStream_t st);
 int launch_scores(const DomdefParams &p, int grid, cudaStream_t st);
-int launch_fwd2(const FilterParams &p, int grid, cudaStream_t st);
-int launch_regions2(const DomdefParams &p, int grid, cudaStream_t st);
-int launch_envelopes2(const DomdefParams &p, int grid, cudaStream_t st);
+int launch_fwd2(const FilterParams &p, int cls, int grid, cudaStream_t st);
+int launch_regions2(const DomdefParams &p, int cls, int grid, cudaStream_t st);
+int launch_envelopes2(const DomdefParams &p, int cls, int grid, cudaStream_t st);
 
 }  // namespace ckm
