@@ -192,6 +192,7 @@ def main():
     ap.add_argument('--impl', default='ckm')
     ap.add_argument('--bins-per-step', type=int, default=BINS_PER_STEP)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--pipeline', type=int, default=2, help='batches in flight per GPU (one engine + host thread each)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
@@ -212,17 +213,19 @@ def main():
     if world > 1:
         dist.barrier()
     db_path, plant = model_db()
-    eng = runtime.engine()
+    NP = max(1, args.pipeline)
+    engs = runtime.engines(NP)
+    eng = engs[0]
     t0 = time.perf_counter()
     models = runtime.models_for(db_path)
     t_load = time.perf_counter() - t0
     info = models.info()
     sumM_all = sum(int(mi.M) for mi in info)
-    # two alternating batches of bins per rank, distinct across ranks
+    # two alternating batches of bins per rank, distinct across ranks; every pipeline slot keeps its own resident copy
     batches = []
     for z in range(2):
         bins, res, off, binof = make_bins(plant, B, 10000 * (rank + 1) + 100 * z)
-        batches.append(dict(bins=bins, res=res, off=off, binof=binof, db=eng.seqdb(res, off, binof, B)))
+        batches.append(dict(bins=bins, res=res, off=off, binof=binof, db=[e_.seqdb(res, off, binof, B) for e_ in engs]))
     # reduction metadata: one marker set per bin = all models (HMM-file semantics), no clans
     nm = models.n
     acc_is_tigr = np.asarray([1 if b'TIGR' in mi.acc else 0 for mi in info], dtype=np.uint8)
@@ -241,7 +244,7 @@ def main():
     set_marker_off = (np.arange(B + 1, dtype=np.int64) * nm)
     set_marker_idx = np.tile(np.arange(nm, dtype=np.int32), B)
 
-    def reduce_hits(batch, hits):
+    def reduce_hits(batch, hits, eng=eng):
         names = [n for b in batch['bins'] for n in b.names]
         key = id(batch)
         if key not in reduce_hits.cache:
@@ -286,35 +289,64 @@ def main():
         dist.all_gather_into_tensor(gather_buf.view(-1), mine)        # NCCL all-gather of the fixed-width QA rows (config #4)
         return gather_buf
 
-    host_ms = {'flush': 0.0, 'search': 0.0, 'reduce': 0.0, 'gather': 0.0}
+    host_ms = {'search': 0.0, 'reduce': 0.0, 'gather': 0.0}
+    gather_lock = threading.Lock()
 
-    def step_resident(i):
-        batch = batches[i % 2]
-        t0 = time.perf_counter()
-        flush_buf.zero_()
-        torch.cuda.synchronize()
+    def step_resident(i, w):
+        """One step on pipeline slot w: inputs resident in HBM."""
+        e_ = engs[w]
+        batch = batches[(i // NP) % 2]
+        flush_buf.zero_()                              # 256 MiB write, asynchronous to the engine streams
         t1 = time.perf_counter()
-        hits = eng.search(models, batch['db'])
-        st = eng.stats()
+        hits = e_.search(models, batch['db'][w])
+        st = e_.stats()
         t2 = time.perf_counter()
-        rows, nmh = reduce_hits(batch, hits)
+        rows, nmh = reduce_hits(batch, hits, e_)
         t3 = time.perf_counter()
-        gather(rows)
+        with gather_lock:
+            gather(rows)
         t4 = time.perf_counter()
-        host_ms['flush'] += 1e3 * (t1 - t0); host_ms['search'] += 1e3 * (t2 - t1); host_ms['reduce'] += 1e3 * (t3 - t2); host_ms['gather'] += 1e3 * (t4 - t3)
-        return hits, st, rows
+        return hits, st, rows, (1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (t4 - t3))
 
-    def step_e2e(i):
-        batch = batches[i % 2]
+    def step_e2e(i, w):
+        """The same through the public API with HOST buffers: H2D of the residues, D2H of the hit table and QA rows."""
+        e_ = engs[w]
+        batch = batches[(i // NP) % 2]
         flush_buf.zero_()
-        db = eng.seqdb(batch['res'], batch['off'], batch['binof'], B)       # host buffers -> HBM
+        db = e_.seqdb(batch['res'], batch['off'], batch['binof'], B)       # host buffers -> HBM
         try:
-            hits = eng.search(models, db)                                   # hit table back on the host
+            hits = e_.search(models, db)                                    # hit table back on the host
+            st = e_.stats()
         finally:
             db.close()
-        rows, nmh = reduce_hits(batch, hits)
-        gather(rows)
-        return hits, rows
+        rows, nmh = reduce_hits(batch, hits, e_)
+        with gather_lock:
+            gather(rows)
+        return hits, st, rows, (0.0, 0.0, 0.0)
+
+    def run_steps(nsteps, fn):
+        """nsteps steps, NP in flight: slot w takes steps w, w+NP, ...  Returns the per-step records in step order."""
+        out = [None] * nsteps
+        errs = []
+
+        def worker(w):
+            try:
+                torch.cuda.set_device(local)           # the current device is per host thread
+                for i in range(w, nsteps, NP):
+                    out[i] = fn(i, w)
+            except BaseException as ex:       # surfaced on the main thread
+                errs.append(ex)
+        if NP == 1:
+            worker(0)
+        else:
+            ths = [threading.Thread(target=worker, args=(w,)) for w in range(NP)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+        if errs:
+            raise errs[0]
+        return out
 
     def sync():
         torch.cuda.synchronize()
@@ -322,34 +354,38 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step_resident(i)
-    for k_ in host_ms:
-        host_ms[k_] = 0.0
+    run_steps(max(args.warmup, 0), step_resident)
     sampler = ClockSampler(local)
     sampler.start()
     sync()
     t0 = time.perf_counter()
+    recs = run_steps(args.steps, step_resident)
+    sync()
+    t_res = time.perf_counter() - t0
     ssv_ms = msv_ms = other_ms = 0.0
-    launches = cells = pairs = resid_sum = 0
-    last = None
-    for i in range(args.steps):
-        hits, st, rows = step_resident(i)
+    launches = cells = pairs = 0
+    for hits, st, rows, hm in recs:
         ssv_ms += st.ms_ssv
         msv_ms += st.ms_msv
         other_ms += st.ms_bias + st.ms_vit + st.ms_fwd + st.ms_domdef
         launches += st.kernel_launches + 5
         cells += st.n_cells
         pairs += st.n_pairs
-        last = (hits, st, rows)
-    sync()
-    t_res = time.perf_counter() - t0
+        for k_, v_ in zip(('search', 'reduce', 'gather'), hm):
+            host_ms[k_] += v_
+    last = recs[-1][:3]
     sync()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        hits_e, rows_e = step_e2e(i)
+    recs_e = run_steps(args.steps, step_e2e)
     sync()
     t_e2e = time.perf_counter() - t0
+    # one batch at a time on one engine: the stage times of an undisturbed search (the SSV roofline is quoted on both)
+    iso = []
+    for i in range(2):
+        iso.append(step_resident(i * NP, 0)[1])
+    sync()
+    iso_ssv_ms = sum(s_.ms_ssv for s_ in iso) / len(iso)
+    iso_st = iso[-1]
     sampler.stop_flag = True
     sampler.join(timeout=2)
     if world > 1:
@@ -371,25 +407,30 @@ def main():
     ssv_s = (ssv_ms / args.steps) / 1000.0
     achieved = alg_bytes_per_step / ssv_s / 1e9
     real_cells = resid * sumM_all
-    h2d = int(batches[0]['db'].residues.nbytes + batches[0]['off'].nbytes + batches[0]['binof'].nbytes)
+    h2d = int(batches[0]['db'][0].residues.nbytes + batches[0]['off'].nbytes + batches[0]['binof'].nbytes)
     d2h = int(hits.nbytes + rows.nbytes)
     line = {"metric": "genomes/hour", "value": value, "unit": "genomes/hour", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16 (SSV) / u8 (MSV) / int16 (Viterbi) / f32 (Forward, domain definition)", "data": "synthetic",
             "config": {"workload": "configs[2] stand-in: synthetic 3 Mb bins (2,900 ORFs, ~0.9 M residues, 0-2 planted homologs per CPR family) x 5,000 HMMs (the 43 real HMMER-calibrated CPR models x 116 replicas under distinct accessions, sum M = %d)" % sumM_all,
                        "bins_per_step": B, "orfs_per_bin": ORFS_PER_BIN, "n_models": nm, "per_gpu_bins_per_step": B, "parallelism": "bins sharded, 1 process/GPU",
-                       "l2": "256 MiB flush write before every step", "model_load_s": t_load},
+                       "batches_in_flight_per_gpu": NP,
+                       "l2": "256 MiB flush write issued before every step; the model tables alone (> 200 MB) exceed L2", "model_load_s": t_load},
             "e2e": {"value": e2e, "unit": "genomes/hour", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": achieved / peaks.get("hbm_gbs"),
                          "traffic": None, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == 'measured' else 'fallback 6650',
                          "kernel": "ssv_kernel<J> (SSV pre-filter, all pairs)", "kernel_ms_per_step": ssv_ms / args.steps,
+                         "isolated": {"kernel_ms": iso_ssv_ms, "achieved": alg_bytes_per_step / (iso_ssv_ms / 1e3) / 1e9,
+                                      "frac": alg_bytes_per_step / (iso_ssv_ms / 1e3) / 1e9 / peaks.get("hbm_gbs"),
+                                      "what": "same kernel, one batch in flight (no other stream on the SMs)"},
                          "note": "the stage is DP-cell bound, not HBM bound (SURVEY.md 8d): see gcups"},
             "gcups": {"real_cells_per_step": real_cells, "tile_cells_per_step": cells / args.steps, "ssv_gcups_real": real_cells / ssv_s / 1e9,
-                      "ssv_gcups_tile": cells / args.steps / ssv_s / 1e9, "smem_bound_gcups_at_1.9GHz": 148 * 51.2 * 1.9,
+                      "ssv_gcups_tile": cells / args.steps / ssv_s / 1e9, "ssv_gcups_real_isolated": real_cells / (iso_ssv_ms / 1e3) / 1e9, "smem_bound_gcups_at_1.9GHz": 148 * 51.2 * 1.9,
                       "stage_ms_per_step": {"ssv": ssv_ms / args.steps, "msv_exact": msv_ms / args.steps, "bias+vit+fwd+domdef": other_ms / args.steps,
                                             "wall_ms_per_step": {k_: v_ / args.steps for k_, v_ in host_ms.items()},
-                                            "last_step": {"bias": st.ms_bias, "vit": st.ms_vit, "fwd": st.ms_fwd, "domdef": st.ms_domdef, "total": st.ms_total}}},
+                                            "isolated_step": {"ssv": iso_st.ms_ssv, "msv_exact": iso_st.ms_msv, "bias": iso_st.ms_bias, "vit": iso_st.ms_vit, "fwd": iso_st.ms_fwd,
+                                                              "domdef": iso_st.ms_domdef, "total": iso_st.ms_total}}},
             "cascade": {"pairs": int(st.n_pairs), "ssv_cand": int(st.n_ssv_cand), "past_msv": int(st.n_past_msv), "past_bias": int(st.n_past_bias),
                         "past_vit": int(st.n_past_vit), "past_fwd": int(st.n_past_fwd), "rows": int(st.n_reported)},
             "clocks": sampler.summary()}

@@ -41,10 +41,19 @@ int ckm_init(int device, ckm_engine **out) {
   }
   CKM_CUDA(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
   for (auto &ev : eng->ev) CKM_CUDA(cudaEventCreate(&ev));
-  for (auto &s : eng->cls) CKM_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  // the class streams carry the latency-bound domain-definition kernels: highest priority, so that their few blocks
+  // are placed ahead of the throughput kernels of another engine sharing the device
+  int prio_lo = 0, prio_hi = 0;
+  CKM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  for (auto &s : eng->cls) CKM_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_hi));
   for (auto &ev : eng->cls_ev) CKM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CKM_CUDA(cudaEventCreateWithFlags(&eng->fan_ev, cudaEventDisableTiming));
   CKM_CUDA(cudaMalloc((void **)&eng->d_counters, 64 * sizeof(int32_t) + 64));
+  {
+    // sequence databases come from the device's stream-ordered pool; keep freed blocks cached for the next batch
+    cudaMemPool_t mp;
+    if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) { uint64_t keep = ~0ull; cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep); }
+  }
   std::memset(&eng->stats, 0, sizeof(eng->stats));
   *out = eng;
   return CKM_OK;
@@ -222,7 +231,7 @@ int ckm_seqdb_create(ckm_engine *e, const uint8_t *residues, const int64_t *seq_
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return db->len[a] > db->len[b]; });
   auto up = [&](void **d, const void *h, size_t bytes) -> int {
-    CKM_CUDA(cudaMalloc(d, std::max<size_t>(bytes, 16)));
+    CKM_CUDA(cudaMallocAsync(d, std::max<size_t>(bytes, 16), e->stream));     // stream-ordered: no device-wide synchronisation
     if (bytes) CKM_CUDA(cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, e->stream));
     return CKM_OK;
   };
@@ -247,9 +256,12 @@ int ckm_seqdb_create(ckm_engine *e, const uint8_t *residues, const int64_t *seq_
 
 void ckm_seqdb_free(ckm_seqdb *db) {
   if (!db) return;
-  if (db->engine) cudaSetDevice(db->engine->device);
-  cudaFree(db->d_res); cudaFree(db->d_off); cudaFree(db->d_len); cudaFree(db->d_bin); cudaFree(db->d_nullsc);
-  cudaFree(db->d_tjb); cudaFree(db->d_msvB); cudaFree(db->d_lenA); cudaFree(db->d_lenB); cudaFree(db->d_tmove_w); cudaFree(db->d_order); cudaFree(db->d_bin_nseq);
+  if (db->engine) {
+    cudaSetDevice(db->engine->device);
+    cudaStream_t st = db->engine->stream;
+    void *ptrs[] = {db->d_res, db->d_off, db->d_len, db->d_bin, db->d_nullsc, db->d_tjb, db->d_msvB, db->d_lenA, db->d_lenB, db->d_tmove_w, db->d_order, db->d_bin_nseq};
+    for (void *q : ptrs) if (q) cudaFreeAsync(q, st);
+  }
   delete db;
 }
 

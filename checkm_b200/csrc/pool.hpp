@@ -6,8 +6,8 @@
 namespace ckm {
 
 // ---- device buffers come from the engine's grow-only cache: no cudaMalloc/cudaFree in the steady state ----
-inline ckm_engine *g_pool_engine = nullptr;
-inline int g_pool_next = 0;
+extern thread_local ckm_engine *g_pool_engine;   // one search per host thread; engines are not shared between threads (defined in search.cu)
+extern thread_local int g_pool_next;
 struct PoolScope {           // every search starts handing out slots from 0 again
   explicit PoolScope(ckm_engine *e) { g_pool_engine = e; g_pool_next = 0; }
   ~PoolScope() { g_pool_engine = nullptr; }

@@ -336,12 +336,12 @@ extern "C" int ckm_genome_check(ckm_engine *e, int32_t nbins, const int64_t *bin
   cudaStream_t st = e->stream;
   const int64_t nsets = bin_set_off[nbins], nm = set_marker_off[nsets];
   void *d_b = nullptr, *d_s = nullptr, *d_c = nullptr, *d_o = nullptr;
-  auto cleanup = [&]() { cudaFree(d_b); cudaFree(d_s); cudaFree(d_c); cudaFree(d_o); };
+  auto cleanup = [&]() { for (void *q : {d_b, d_s, d_c, d_o}) if (q) cudaFreeAsync(q, st); };       // stream-ordered pool: no device-wide synchronisation
 #define GCUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #call); } } while (0)
-  GCUDA(cudaMalloc(&d_b, sizeof(int64_t) * (nbins + 1)));
-  GCUDA(cudaMalloc(&d_s, sizeof(int64_t) * (size_t)(nsets + 1)));
-  GCUDA(cudaMalloc(&d_c, sizeof(int32_t) * (size_t)std::max<int64_t>(nm, 1)));
-  GCUDA(cudaMalloc(&d_o, sizeof(ckm_qa_row) * nbins));
+  GCUDA(cudaMallocAsync(&d_b, sizeof(int64_t) * (nbins + 1), st));
+  GCUDA(cudaMallocAsync(&d_s, sizeof(int64_t) * (size_t)(nsets + 1), st));
+  GCUDA(cudaMallocAsync(&d_c, sizeof(int32_t) * (size_t)std::max<int64_t>(nm, 1), st));
+  GCUDA(cudaMallocAsync(&d_o, sizeof(ckm_qa_row) * nbins, st));
   GCUDA(cudaMemcpyAsync(d_b, bin_set_off, sizeof(int64_t) * (nbins + 1), cudaMemcpyHostToDevice, st));
   GCUDA(cudaMemcpyAsync(d_s, set_marker_off, sizeof(int64_t) * (size_t)(nsets + 1), cudaMemcpyHostToDevice, st));
   if (nm > 0) GCUDA(cudaMemcpyAsync(d_c, marker_count, sizeof(int32_t) * (size_t)nm, cudaMemcpyHostToDevice, st));
@@ -397,8 +397,8 @@ extern "C" int ckm_reduce(ckm_engine *e, int32_t nmodels_in, int32_t nseq_in, in
   std::vector<int64_t> zero_off(nbins + 1, 0), zero_set(1, 0);
 
   std::vector<void *> frees;
-  auto dalloc = [&](size_t bytes) -> void * { void *p = nullptr; if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) return nullptr; frees.push_back(p); return p; };
-  auto cleanup = [&]() { for (void *p : frees) cudaFree(p); };
+  auto dalloc = [&](size_t bytes) -> void * { void *p = nullptr; if (cudaMallocAsync(&p, std::max<size_t>(bytes, 16), st) != cudaSuccess) return nullptr; frees.push_back(p); return p; };
+  auto cleanup = [&]() { for (void *p : frees) cudaFreeAsync(p, st); };
 #define RCUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #call); } } while (0)
 #define UP(dst, src, bytes) do { dst = (decltype(dst))dalloc(bytes); if (!dst) { cleanup(); set_error("ckm_reduce: out of device memory"); return CKM_ENOMEM; } if ((bytes) > 0) RCUDA(cudaMemcpyAsync((void *)dst, src, bytes, cudaMemcpyHostToDevice, st)); } while (0)
   RParams p;

@@ -13,6 +13,9 @@ using namespace ckm;
 
 namespace ckm {
 
+thread_local ckm_engine *g_pool_engine = nullptr;
+thread_local int g_pool_next = 0;
+
 static bool use_blocked_kernels();
 static int fan_out(ckm_engine *e);
 static int fan_in(ckm_engine *e);
@@ -281,8 +284,11 @@ static int fan_in(ckm_engine *e) {
 }
 
 static std::vector<float> &logsum_table() {
-  static std::vector<float> t;
-  if (t.empty()) { t.resize(16000); for (int i = 0; i < 16000; ++i) t[i] = (float)std::log(1.0 + std::exp((double)-i / 1000.0)); }
+  static std::vector<float> t = [] {
+    std::vector<float> v(16000);
+    for (int i = 0; i < 16000; ++i) v[i] = (float)std::log(1.0 + std::exp((double)-i / 1000.0));
+    return v;
+  }();
   return t;
 }
 

@@ -7,6 +7,7 @@ import os
 from .engine import Engine
 
 _engine = None
+_extra = []
 _models = {}
 
 
@@ -23,6 +24,17 @@ def engine():
     if _engine is None:
         _engine = Engine(device_index())
     return _engine
+
+
+def engines(n):
+    """`n` engines on this process's GPU for pipelined batches: engine 0 is the process-wide one, the others are extra
+    streams + workspaces on the same device.  One host thread drives one engine at a time (include/ckm.h); model
+    databases are device-resident and shared by all of them."""
+    global _extra
+    first = engine()
+    while len(_extra) < n - 1:
+        _extra.append(Engine(first.device))
+    return [first] + _extra[:n - 1]
 
 
 def models_for(path):
@@ -43,6 +55,8 @@ def shutdown():
     for _, m in _models.values():
         m.close()
     _models.clear()
+    while _extra:
+        _extra.pop().close()
     if _engine is not None:
         _engine.close()
         _engine = None
