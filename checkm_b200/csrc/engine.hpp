@@ -49,7 +49,8 @@ struct ModelScalars {
   int32_t off_cells;     // offset (in table "columns") of this model in the per-model tables; column stride Mpad
   int32_t Mpad;          // (M+1) rounded up to 32
   uint8_t tbm_b, tec_b, base_b, bias_b;
-  int16_t base_w, xw_e_loop, xw_e_move, pad16;
+  int16_t base_w, xw_e_loop, xw_e_move;
+  int16_t msv2_ok;       // 1: the lane-blocked MSV kernel applies (vq != 0 and base_b + bias_b < 255, so its adds cannot saturate)
   float   scale_b, scale_w;
   float   evparam[6];
   int32_t ddbound_w;     // lazy-F bound of the Viterbi filter
@@ -82,6 +83,7 @@ struct ckm_models {
   float    *d_bias_eo = nullptr;  // per model [KPAD][2]
   // lane-blocked copies for the register-resident survivor kernels: lane l owns positions k = l*vq + q + 1
   uint4    *d_twb = nullptr;      // per model [vq][32] : 8 int16 transitions of cell (q, lane)
+  uint32_t *d_rmb = nullptr;      // per model [KPAD][vq/2][32] : two int16 MSV emission gains bias - cost (q = j, vq/2 + j)
   uint32_t *d_rwb = nullptr;      // per model [KPAD][vq/2][32] : two int16 emissions (q = 2j, 2j+1)
   float4   *d_tfb = nullptr;      // per model [vq][32][2] : 8 fp32 transitions
   float    *d_rfb = nullptr;      // per model [KPAD][vq][32] : fp32 emission odds

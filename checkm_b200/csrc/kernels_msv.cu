@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(MSV_WARPS * 32) msv_exact_kernel(MsvParams p) 
     const int2 pr = p.cand[c];
     const int s = pr.x, m = pr.y;
     const ModelScalars ms = p.ms[m];
+    if (ms.msv2_ok) continue;               // handled by msv2_kernel<Q>
     const int M = ms.M, L = p.len[s];
     const uint8_t *res = p.res + p.off[s];
     const uint8_t *rbv = p.rbv + (int64_t)ms.off_cells * KPAD;
@@ -278,6 +279,122 @@ __global__ void __launch_bounds__(MSV_WARPS * 32) msv_exact_kernel(MsvParams p) 
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact MSV, lane-blocked: lane l keeps model positions l*Q+1 .. l*Q+Q of the row in Q/2 registers of two int16
+// (word j = positions j and Q/2+j of the block, so the k-1 dependency is a register rename plus one shuffle and one
+// byte permute per row).  The byte recurrence  sv = sat0(sat255(max(sv', xB) + bias) - cost)  is evaluated as
+// max(max(sv', xB) + (bias - cost), 0): the 255 clamp cannot fire before the row-level overflow test does (every
+// operand is <= the previous row's xE or xB, both < 255 - bias; models with base + bias >= 255 stay on the byte kernel),
+// so the bytes are those of msv_exact_kernel.  2 packed instructions per 2 cells instead of ~8 scalar ones per cell.
+// ------------------------------------------------------------------------------------------------
+template <int Q>
+__global__ void __launch_bounds__(128) msv2_kernel(MsvParams p) {
+  constexpr int H = Q / 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int ncand = min(*p.cand_count, p.cand_cap);
+  for (int c = blockIdx.x * wpb + warp; c < ncand; c += gridDim.x * wpb) {
+    const int2 pr = p.cand[c];
+    const int s = pr.x, m = pr.y;
+    const ModelScalars ms = p.ms[m];
+    if (ms.vq != Q || !ms.msv2_ok) continue;
+    const int L = p.len[s];
+    const uint32_t *rmb = p.rmb + ms.blk_off * 32 * (KPAD / 2) + lane;
+    const int tjb = p.tjb[s];
+    const int tjbm = min(tjb + (int)ms.tbm_b, 255);
+    const int bias = ms.bias_b, base = ms.base_b, tec = ms.tec_b;
+    uint32_t sv[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) sv[j] = 0u;
+    int xJ = 0, xB = max(base - tjbm, 0);
+    uint32_t XB = (uint32_t)xB * 0x00010001u;
+    bool overflow = false;
+    const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + p.off[s]);
+    const int nblk = (L + 15) >> 4;
+    for (int b = 0; b < nblk && !overflow; ++b) {
+      const uint4 r16 = __ldg(rp + b);
+      const uint32_t w4[4] = {r16.x, r16.y, r16.z, r16.w};
+      const int rows = min(16, L - b * 16);
+      uint32_t e[H], en[H];
+      {
+        const uint32_t x0 = w4[0] & 0xffu;
+#pragma unroll
+        for (int j = 0; j < H; ++j) en[j] = __ldg(rmb + (x0 * H + j) * 32);
+      }
+      for (int r = 0; r < rows; ++r) {
+#pragma unroll
+        for (int j = 0; j < H; ++j) e[j] = en[j];
+        if (r + 1 < rows) {                       // next row's gains are in flight while this row computes
+          const uint32_t xn = (w4[(r + 1) >> 2] >> (8 * ((r + 1) & 3))) & 0xffu;
+#pragma unroll
+          for (int j = 0; j < H; ++j) en[j] = __ldg(rmb + (xn * H + j) * 32);
+        }
+        uint32_t up = __shfl_up_sync(0xffffffffu, sv[H - 1], 1);
+        if (lane == 0) up = 0u;
+        const uint32_t in0 = __byte_perm(up, sv[H - 1], 0x5432);     // lo: position below my block, hi: my position Q/2
+#pragma unroll
+        for (int j = H - 1; j >= 1; --j) sv[j] = __viaddmax_s16x2(__vmaxs2(sv[j - 1], XB), e[j], 0u);
+        sv[0] = __viaddmax_s16x2(__vmaxs2(in0, XB), e[0], 0u);
+        uint32_t xEv = sv[0];
+        if (H == 1) { }
+        else if (H & 1) {
+#pragma unroll
+          for (int j = 1; j + 1 < H; j += 2) xEv = __vimax3_s16x2(xEv, sv[j], sv[j + 1]);
+        } else {
+          xEv = __vmaxs2(xEv, sv[1]);
+#pragma unroll
+          for (int j = 2; j + 1 < H; j += 2) xEv = __vimax3_s16x2(xEv, sv[j], sv[j + 1]);
+        }
+        int xE = max((int)(xEv & 0xffffu), (int)(xEv >> 16));
+        xE = __reduce_max_sync(0xffffffffu, xE);
+        if (xE + bias >= 255) { overflow = true; break; }
+        xE = max(xE - tec, 0);
+        xJ = max(xJ, xE);
+        xB = max(max(base, xJ) - tjbm, 0);
+        XB = (uint32_t)xB * 0x00010001u;
+      }
+    }
+    if (lane == 0) {
+      float usc;
+      if (overflow) usc = INFINITY;
+      else {
+        usc = ((float)(xJ - tjb) - (float)base);
+        usc = __fdiv_rn(usc, ms.scale_b);
+        usc = __fsub_rn(usc, 3.0f);
+      }
+      if (p.xj_dense != nullptr) p.xj_dense[(int64_t)p.model_slot[m] * p.nseq + s] = overflow ? 256 : xJ;
+      const float nullsc = p.nullsc[s];
+      const float seq_score = __fdiv_rn(__fsub_rn(usc, nullsc), 0.69314718055994529f);
+      const double P = gumbel_surv((double)seq_score, (double)ms.evparam[0], (double)ms.evparam[1]);
+      if (P <= p.F1) {
+        const int pos = atomicAdd(p.out_count, 1);
+        if (pos < p.out_cap) {
+          Candidate cd;
+          cd.seq = s; cd.model = m; cd.usc = usc; cd.filtersc = nullsc; cd.vitsc = 0.f; cd.fwdsc = 0.f; cd.P = P;
+          p.out[pos] = cd;
+        }
+      }
+    }
+  }
+}
+
+int launch_msv2(const MsvParams &p, int cls, int grid, cudaStream_t stream) {
+  switch (cls) {
+    case 0: msv2_kernel<2><<<grid, 128, 0, stream>>>(p); break;
+    case 1: msv2_kernel<4><<<grid, 128, 0, stream>>>(p); break;
+    case 2: msv2_kernel<6><<<grid, 128, 0, stream>>>(p); break;
+    case 3: msv2_kernel<8><<<grid, 128, 0, stream>>>(p); break;
+    case 4: msv2_kernel<12><<<grid, 128, 0, stream>>>(p); break;
+    case 5: msv2_kernel<16><<<grid, 128, 0, stream>>>(p); break;
+    case 6: msv2_kernel<20><<<grid, 128, 0, stream>>>(p); break;
+    case 7: msv2_kernel<24><<<grid, 128, 0, stream>>>(p); break;
+    case 8: msv2_kernel<28><<<grid, 128, 0, stream>>>(p); break;
+    case 9: msv2_kernel<32><<<grid, 128, 0, stream>>>(p); break;
+    default: set_error("launch_msv2: bad class"); return CKM_EINVAL;
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? CKM_OK : cuda_fail(e, "msv2_kernel launch");
 }
 
 int launch_msv_exact(const MsvParams &p, int grid, cudaStream_t stream) {

@@ -175,6 +175,7 @@ int models_build_device(ckm_models &db) {
     s.ddbound_w = m.ddbound_w;
     s.vq = (m.M <= 64) ? 2 : (m.M <= 128) ? 4 : (m.M <= 192) ? 6 : (m.M <= 256) ? 8 : (m.M <= 384) ? 12 : (m.M <= 512) ? 16 : (m.M <= 640) ? 20 : (m.M <= 768) ? 24 : (m.M <= 896) ? 28 : (m.M <= 1024) ? 32 : 0;
     s.blk_off = blk_units;
+    s.msv2_ok = (s.vq != 0 && (int)m.base_b + (int)m.bias_b < 255) ? 1 : 0;
     blk_units += s.vq;
     db.maxM = std::max(db.maxM, m.M);
   }
@@ -202,6 +203,7 @@ int models_build_device(ckm_models &db) {
   // lane-blocked tables
   std::vector<uint4> twb((size_t)std::max<int64_t>(blk_units, 1) * 32);
   std::vector<uint32_t> rwb((size_t)std::max<int64_t>(blk_units, 1) * 32 * KPAD / 2 + 32);
+  std::vector<uint32_t> rmb((size_t)std::max<int64_t>(blk_units, 1) * 32 * KPAD / 2 + 32);
   std::vector<float4> tfb((size_t)std::max<int64_t>(blk_units, 1) * 32 * 2);
   std::vector<float> rfb((size_t)std::max<int64_t>(blk_units, 1) * 32 * KPAD);
   for (int i = 0; i < n; ++i) {
@@ -228,12 +230,19 @@ int models_build_device(ckm_models &db) {
           uint32_t &w = rwb[(size_t)s.blk_off * 32 * KPAD / 2 + ((size_t)x * (Q / 2) + (q >> 1)) * 32 + lane];
           if (q & 1) w = (w & 0x0000ffffu) | ((uint32_t)(uint16_t)ew << 16); else w = (w & 0xffff0000u) | (uint16_t)ew;
           rfb[(size_t)s.blk_off * 32 * KPAD + ((size_t)x * Q + q) * 32 + lane] = ef;
+          // MSV gains bias - cost; word j of a lane pairs its positions j and Q/2 + j, so a one-position shift stays
+          // inside the register file.  Positions past M can never score.
+          const int cost = (k <= m.M && x < KP) ? (int)m.rbv[(size_t)x * W1 + k] : 255;
+          const int16_t eg = (k <= m.M) ? (int16_t)((int)m.bias_b - cost) : (int16_t)-20000;
+          uint32_t &wm = rmb[(size_t)s.blk_off * 32 * KPAD / 2 + ((size_t)x * (Q / 2) + (q % (Q / 2))) * 32 + lane];
+          if (q >= Q / 2) wm = (wm & 0x0000ffffu) | ((uint32_t)(uint16_t)eg << 16); else wm = (wm & 0xffff0000u) | (uint16_t)eg;
         }
       }
   }
   int st;
   if ((st = upload(&db.d_twb, twb))) return st;
   if ((st = upload(&db.d_rwb, rwb))) return st;
+  if ((st = upload(&db.d_rmb, rmb))) return st;
   if ((st = upload(&db.d_tfb, tfb))) return st;
   if ((st = upload(&db.d_rfb, rfb))) return st;
   if ((st = upload(&db.d_scalars, sc))) return st;
@@ -257,7 +266,7 @@ int models_build_device(ckm_models &db) {
 
 void models_free_device(ckm_models &db) {
   cudaFree(db.d_scalars); cudaFree(db.d_rbv); cudaFree(db.d_rwv); cudaFree(db.d_twv); cudaFree(db.d_rfv); cudaFree(db.d_tfv);
-  cudaFree(db.d_bias_eo); cudaFree(db.d_twb); cudaFree(db.d_rwb); cudaFree(db.d_tfb); cudaFree(db.d_rfb); cudaFree(db.d_tile_blob); cudaFree(db.d_tiles); cudaFree(db.d_tile_models); cudaFree(db.d_groups);
+  cudaFree(db.d_bias_eo); cudaFree(db.d_twb); cudaFree(db.d_rwb); cudaFree(db.d_rmb); cudaFree(db.d_tfb); cudaFree(db.d_rfb); cudaFree(db.d_tile_blob); cudaFree(db.d_tiles); cudaFree(db.d_tile_models); cudaFree(db.d_groups);
   cudaFree(db.d_chain_first_tile); cudaFree(db.d_chain_ntiles);
 }
 

@@ -137,14 +137,17 @@ static int run_stage1(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
   {
     MsvParams p{};
     p.res = db->d_res; p.off = db->d_off; p.len = db->d_len; p.nullsc = db->d_nullsc; p.tjb = db->d_tjb;
-    p.ms = m->d_scalars; p.rbv = m->d_rbv;
+    p.ms = m->d_scalars; p.rbv = m->d_rbv; p.rmb = m->d_rmb;
     p.cand = s1.cand.as<int2>(); p.cand_count = e->d_counters + CTR_CAND; p.cand_cap = s1.cand_cap;
     p.out = s1.pass.as<Candidate>(); p.out_count = e->d_counters + CTR_MSV; p.out_cap = s1.pass_cap;
     p.xj_dense = xj_dense; p.model_slot = am.model_slot.as<int32_t>(); p.nseq = db->nseq;
     p.row_bytes = (m->maxM + 2 + 15) / 16 * 16;
     p.F1 = 0.02;
-    if ((rc = launch_msv_exact(p, nsm * 4, st))) return rc;
-    e->stats.kernel_launches++;
+    if ((rc = fan_out(e))) return rc;
+    for (int c = 0; c < N_BLK_CLASSES; ++c) if ((rc = launch_msv2(p, c, nsm * 16, e->cls[c]))) return rc;
+    if ((rc = launch_msv_exact(p, nsm * 4, e->cls[N_BLK_CLASSES]))) return rc;
+    if ((rc = fan_in(e))) return rc;
+    e->stats.kernel_launches += 1 + N_BLK_CLASSES;
   }
   CKM_CUDA(cudaEventRecord(e->ev[2], st));
   return CKM_OK;

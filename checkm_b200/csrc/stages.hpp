@@ -32,7 +32,7 @@ int launch_ssv(int J, const SsvParams &p, int grid, size_t smem_bytes, cudaStrea
 struct MsvParams {
   const uint8_t *res; const int64_t *off; const int32_t *len;
   const float *nullsc; const int32_t *tjb;
-  const ModelScalars *ms; const uint8_t *rbv;
+  const ModelScalars *ms; const uint8_t *rbv; const uint32_t *rmb;
   const int2 *cand; const int32_t *cand_count; int32_t cand_cap;
   Candidate *out; int32_t *out_count; int32_t out_cap;
   int32_t *xj_dense;           // optional [nmodel_slots][nseq] dense output for parity tests (null in production)
@@ -42,7 +42,8 @@ struct MsvParams {
   double F1;
 };
 
-int launch_msv_exact(const MsvParams &p, int grid, cudaStream_t stream);
+int launch_msv_exact(const MsvParams &p, int grid, cudaStream_t stream);           // models without a lane-block class
+int launch_msv2(const MsvParams &p, int cls, int grid, cudaStream_t stream);       // lane-blocked, class index 0..9
 
 // ---- stages 2-4: bias filter, ViterbiFilter, ForwardParser on the survivors ----
 constexpr int VIT_WARPS = 4;
