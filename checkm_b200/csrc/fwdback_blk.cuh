@@ -40,7 +40,10 @@ __device__ __forceinline__ void blk_model_load(BlkModel<Q, TSMEM> &bm, const Mod
 }
 
 // Forward.  xmx: optional (L+1) x 6 special-state rows; full: optional blocked matrix.  Returns the score (nats).
-template <int Q, bool TSMEM, bool FULL>
+// STORE_D = false: the D plane of the full matrix is not written (posterior decoding reads M and I only).
+// The emission row of residue i+1 is fetched while row i is computed (one row of look-ahead in registers), so the
+// table latency (L2 for the wide classes) is off the row-to-row critical path.
+template <int Q, bool TSMEM, bool FULL, bool STORE_D = true>
 __device__ __forceinline__ float forward_blk(const BlkModel<Q, TSMEM> &bm, const uint8_t *__restrict__ res, int L, const Specials sp,
                                              float *xmx, float *full) {
   const int lane = bm.lane;
@@ -53,9 +56,21 @@ __device__ __forceinline__ float forward_blk(const BlkModel<Q, TSMEM> &bm, const
   }
   float xE = 0.0f, xN = 1.0f, xJ = 0.0f, xB = sp.nmove, xC = 0.0f, totscale = 0.0f;
   if (xmx != nullptr && lane == 0) { xmx[X_E] = xE; xmx[X_N] = xN; xmx[X_J] = xJ; xmx[X_B] = xB; xmx[X_C] = xC; xmx[X_SCALE] = 1.0f; }
+  float ecur[Q];
+  {
+    const float *rp = bm.rfb + (size_t)((L >= 1) ? __ldg(res) : 0) * Q * 32;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) ecur[q] = __ldg(rp + q * 32);
+  }
+  int xnext = (L >= 2) ? __ldg(res + 1) : 0;
   for (int i = 1; i <= L; ++i) {
-    const int x = res[i - 1];
-    const float *rp = bm.rfb + (size_t)x * Q * 32;
+    float enext[Q];
+    {
+      const float *rp = bm.rfb + (size_t)xnext * Q * 32;
+#pragma unroll
+      for (int q = 0; q < Q; ++q) enext[q] = __ldg(rp + q * 32);
+      xnext = (i + 2 <= L) ? __ldg(res + i + 1) : 0;
+    }
     float pm_in = __shfl_up_sync(0xffffffffu, Mx[Q - 1], 1), pi_in = __shfl_up_sync(0xffffffffu, Ix[Q - 1], 1), pd_in = __shfl_up_sync(0xffffffffu, Dx[Q - 1], 1);
     if (lane == 0) { pm_in = 0.0f; pi_in = 0.0f; pd_in = 0.0f; }
     float md[Q], esum = 0.0f;
@@ -67,7 +82,7 @@ __device__ __forceinline__ float forward_blk(const BlkModel<Q, TSMEM> &bm, const
       sv += pm * t0.y;
       sv += pi * t0.z;
       sv += pd * t0.w;
-      sv *= __ldg(rp + q * 32);
+      sv *= ecur[q];
       const float nI = Mx[q] * t1.y + Ix[q] * t1.z;
       md[q] = sv * t1.x;
       Mx[q] = sv; Ix[q] = nI;
@@ -110,18 +125,24 @@ __device__ __forceinline__ float forward_blk(const BlkModel<Q, TSMEM> &bm, const
     if (FULL) {
       float *fr = full + (size_t)i * 3 * Q * 32 + lane;
 #pragma unroll
-      for (int q = 0; q < Q; ++q) { fr[q * 32] = Mx[q]; fr[(Q + q) * 32] = Dx[q]; fr[(2 * Q + q) * 32] = Ix[q]; }
+      for (int q = 0; q < Q; ++q) { fr[q * 32] = Mx[q]; if (STORE_D) fr[(Q + q) * 32] = Dx[q]; fr[(2 * Q + q) * 32] = Ix[q]; }
     }
     if (xmx != nullptr && lane == 0) {
       float *xr = xmx + (size_t)i * X_NX;
       xr[X_E] = xE; xr[X_N] = xN; xr[X_J] = xJ; xr[X_B] = xB; xr[X_C] = xC; xr[X_SCALE] = scale;
     }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) ecur[q] = enext[q];
   }
   return totscale + (float)log((double)(xC * sp.nmove));
 }
 
-// Backward with the Forward pass's per-row scale factors.  bxmx: (L+1) x 6 rows out; full: optional blocked matrix.
-template <int Q, bool TSMEM, bool FULL>
+// Backward with the Forward pass's per-row scale factors.  bxmx: (L+1) x 6 rows out.
+// MODE 0: no matrix.  MODE 1: the Backward matrix is stored in `full` (blocked layout).  MODE 2: `full` holds the
+// Forward matrix (M and I planes); row i is replaced IN PLACE by the products F(i,k) B(i,k) -- the posterior
+// probabilities up to the per-row factor totr, which the consumers apply -- so no Backward matrix is ever written.
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <int Q, bool TSMEM, int MODE>
 __device__ __forceinline__ void backward_blk(const BlkModel<Q, TSMEM> &bm, const uint8_t *__restrict__ res, int L, const Specials sp,
                                              const float *fxmx, float *bxmx, float *full) {
   const int lane = bm.lane, M = bm.M;
@@ -129,8 +150,22 @@ __device__ __forceinline__ void backward_blk(const BlkModel<Q, TSMEM> &bm, const
 #pragma unroll
   for (int q = 0; q < Q; ++q) { Mx[q] = 0.0f; Ix[q] = 0.0f; Dx[q] = 0.0f; }
   float xC = 0.0f, xE = 0.0f, xJ = 0.0f, xN = 0.0f, xB = 0.0f;
+  float ecur[Q];          // emission row of residue x_{i+1}; fetched one iteration ahead
+#pragma unroll
+  for (int q = 0; q < Q; ++q) ecur[q] = 0.0f;
+  int xnext = (L >= 1) ? __ldg(res + L - 1) : 0;
   for (int i = L; i >= 0; --i) {
-    const float *rp = (i < L) ? bm.rfb + (size_t)res[i] * Q * 32 : nullptr;      // residue x_{i+1}
+    float enext[Q];
+    {
+      const float *rp = bm.rfb + (size_t)xnext * Q * 32;
+#pragma unroll
+      for (int q = 0; q < Q; ++q) enext[q] = __ldg(rp + q * 32);
+      xnext = (i >= 2) ? __ldg(res + i - 2) : 0;
+    }
+    if (MODE == 2 && i >= 3) {     // pull row i-2 of the Forward matrix towards L2 (M plane, I plane: Q lines each)
+      const float *fr = full + (size_t)(i - 2) * 3 * Q * 32;
+      if (lane < Q) { prefetch_l2(fr + lane * 32); prefetch_l2(fr + (2 * Q + lane) * 32); }
+    }
     float em[Q];                                                                  // e(k, x_{i+1}) M(i+1, k)
     if (i == L) {
       xC = sp.nmove; xE = xC * sp.emove; xB = 0.0f; xJ = 0.0f; xN = 0.0f;
@@ -139,7 +174,7 @@ __device__ __forceinline__ void backward_blk(const BlkModel<Q, TSMEM> &bm, const
     } else {
       float part = 0.0f;
 #pragma unroll
-      for (int q = 0; q < Q; ++q) { em[q] = Mx[q] * __ldg(rp + q * 32); part += em[q] * bm.T0(q).x; }
+      for (int q = 0; q < Q; ++q) { em[q] = Mx[q] * ecur[q]; part += em[q] * bm.T0(q).x; }
       xB = warp_sum_float(part);
       xC = xC * sp.nloop;
       xJ = (xB * sp.nmove) + (xJ * sp.nloop);
@@ -204,15 +239,25 @@ __device__ __forceinline__ void backward_blk(const BlkModel<Q, TSMEM> &bm, const
 #pragma unroll
       for (int q = 0; q < Q; ++q) { Mx[q] = 0.0f; Ix[q] = 0.0f; Dx[q] = 0.0f; }
     }
-    if (FULL) {
+    if (MODE == 1) {
       float *fr = full + (size_t)i * 3 * Q * 32 + lane;
 #pragma unroll
       for (int q = 0; q < Q; ++q) { fr[q * 32] = Mx[q]; fr[(Q + q) * 32] = Dx[q]; fr[(2 * Q + q) * 32] = Ix[q]; }
+    }
+    if (MODE == 2 && i >= 1) {
+      float *fr = full + (size_t)i * 3 * Q * 32 + lane;
+      float fm[Q], fi[Q];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) { fm[q] = fr[q * 32]; fi[q] = fr[(2 * Q + q) * 32]; }      // all loads first, then the stores
+#pragma unroll
+      for (int q = 0; q < Q; ++q) { fr[q * 32] = fm[q] * Mx[q]; fr[(2 * Q + q) * 32] = fi[q] * Ix[q]; }
     }
     if (bxmx != nullptr && lane == 0) {
       float *xr = bxmx + (size_t)i * X_NX;
       xr[X_E] = xE; xr[X_N] = xN; xr[X_J] = xJ; xr[X_B] = xB; xr[X_C] = xC; xr[X_SCALE] = s;
     }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) ecur[q] = enext[q];
   }
 }
 

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(BLK_WARPS * 32) regions2_kernel(DomdefParams p
     float *xf = p.xf + pw.row_off * X_NX, *xb = p.xb + pw.row_off * X_NX;
     forward_blk<Q, TSMEM, false>(bm, res, L, sp, xf, nullptr);
     __syncwarp();
-    backward_blk<Q, TSMEM, false>(bm, res, L, sp, xf, xb, nullptr);
+    backward_blk<Q, TSMEM, 0>(bm, res, L, sp, xf, xb, nullptr);
     __syncwarp();
     regions_tail(p, pi, L, sp, xf, xb, p.btot + pw.row_off, p.etot + pw.row_off, p.mocc + pw.row_off, p.n2sc + pw.row_off, lane);
     __syncwarp();
@@ -101,24 +101,29 @@ __global__ void __launch_bounds__(BLK_WARPS * 32) envelope2_kernel(DomdefParams 
     float *xf = Bm + mat, *xb = xf + (int64_t)(Ld + 1) * X_NX, *pps = xb + (int64_t)(Ld + 1) * X_NX;
     float *xo = xf;
     float *n2sc = p.n2sc + pw.row_off;
-    const float envsc = forward_blk<Q, TSMEM, true>(bm, res, Ld, sp, xf, F);
+    // F: Forward matrix (M, I planes) -> replaced in place by F.B during the Backward pass; Bm: later the OA matrix
+    const float envsc = forward_blk<Q, TSMEM, true, false>(bm, res, Ld, sp, xf, F);
     __syncwarp();
-    backward_blk<Q, TSMEM, true>(bm, res, Ld, sp, xf, xb, Bm);
+    backward_blk<Q, TSMEM, 2>(bm, res, Ld, sp, xf, xb, F);
     __syncwarp();
-    // ---- posterior decoding (pp overwrites the Backward matrix) + expected state usage for null2 ----
+    // ---- posterior decoding: pp(r,k) = (F.B)(r,k) * totr; expected state usage for null2 (summed in row order) ----
     const float scaleproduct = __fdiv_rn(1.0f, xb[X_N]);
     float em[Q], ein[Q];
 #pragma unroll
     for (int q = 0; q < Q; ++q) { em[q] = 0.0f; ein[q] = 0.0f; }
     for (int r = 1; r <= Ld; ++r) {
+      if (r + 2 <= Ld && lane < Q) {
+        const float *fn = F + (int64_t)(r + 2) * 3 * QW;
+        prefetch_l2(fn + lane * 32); prefetch_l2(fn + (2 * Q + lane) * 32);
+      }
       const float totr = scaleproduct * xf[(int64_t)r * X_NX + X_SCALE];
       const float *fr = F + (int64_t)r * 3 * QW + lane;
-      float *br = Bm + (int64_t)r * 3 * QW + lane;
+      float vm[Q], vi[Q];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) { vm[q] = fr[q * 32]; vi[q] = fr[(2 * Q + q) * 32]; }
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
-        const float pm = fr[q * 32] * br[q * 32] * totr;
-        const float pi = fr[(2 * Q + q) * 32] * br[(2 * Q + q) * 32] * totr;
-        br[q * 32] = pm; br[(2 * Q + q) * 32] = pi;        // the D plane is never read again
+        const float pm = vm[q] * totr, pi = vi[q] * totr;
         em[q] = (r == 1) ? pm : em[q] + pm;
         ein[q] = (r == 1) ? pi : ein[q] + pi;
       }
@@ -177,12 +182,20 @@ __global__ void __launch_bounds__(BLK_WARPS * 32) envelope2_kernel(DomdefParams 
 #pragma unroll
       for (int q = 0; q < Q; ++q) { oM[q] = NINF; oI[q] = NINF; oD[q] = NINF; }
 #pragma unroll
-      for (int z = 0; z < 3 * Q; ++z) F[z * 32 + lane] = NINF;
+      for (int z = 0; z < 3 * Q; ++z) Bm[z * 32 + lane] = NINF;
       float oE = NINF, oN = 0.0f, oJ = NINF, oC = NINF, oB = (sp.nmove > 0.0f) ? 0.0f : NINF;
       if (lane == 0) { xo[X_E] = oE; xo[X_N] = oN; xo[X_J] = oJ; xo[X_B] = oB; xo[X_C] = oC; }
       for (int r = 1; r <= Ld; ++r) {
-        const float *ppr = Bm + (int64_t)r * 3 * QW + lane;
-        float *orow = F + (int64_t)r * 3 * QW + lane;
+        if (r + 2 <= Ld && lane < Q) {
+          const float *fn = F + (int64_t)(r + 2) * 3 * QW;
+          prefetch_l2(fn + lane * 32); prefetch_l2(fn + (2 * Q + lane) * 32);
+        }
+        const float totr = scaleproduct * xf[(int64_t)r * X_NX + X_SCALE];      // X_SCALE survives the xo writes below
+        const float *ppr = F + (int64_t)r * 3 * QW + lane;
+        float *orow = Bm + (int64_t)r * 3 * QW + lane;
+        float ppm[Q], ppi[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) { ppm[q] = ppr[q * 32]; ppi[q] = ppr[(2 * Q + q) * 32]; }
         float pm_in = __shfl_up_sync(0xffffffffu, oM[Q - 1], 1), pi_in = __shfl_up_sync(0xffffffffu, oI[Q - 1], 1), pd_in = __shfl_up_sync(0xffffffffu, oD[Q - 1], 1);
         if (lane == 0) { pm_in = NINF; pi_in = NINF; pd_in = NINF; }
         float a[Q]; bool ps[Q];
@@ -196,9 +209,9 @@ __global__ void __launch_bounds__(BLK_WARPS * 32) envelope2_kernel(DomdefParams 
           sv = fmaxf(sv, (t0.y > 0.0f) ? pm : 0.0f);
           sv = fmaxf(sv, (t0.z > 0.0f) ? pi : 0.0f);
           sv = fmaxf(sv, (t0.w > 0.0f) ? pd : 0.0f);
-          sv += ppr[q * 32];
+          sv += ppm[q] * totr;
           if (!in) sv = NINF;
-          const float nI = in ? fmaxf((t1.y > 0.0f) ? oM[q] : 0.0f, (t1.z > 0.0f) ? oI[q] : 0.0f) + ppr[(2 * Q + q) * 32] : NINF;
+          const float nI = in ? fmaxf((t1.y > 0.0f) ? oM[q] : 0.0f, (t1.z > 0.0f) ? oI[q] : 0.0f) + ppi[q] * totr : NINF;
           a[q] = (t1.x > 0.0f) ? sv : 0.0f;
           ps[q] = (t1.w > 0.0f);
           if (!in) { a[q] = NINF; ps[q] = true; }
@@ -247,7 +260,7 @@ __global__ void __launch_bounds__(BLK_WARPS * 32) envelope2_kernel(DomdefParams 
     // ---- OA traceback (warp-uniform walk; cell (k) lives at q = (k-1) % Q, lane = (k-1) / Q) ----
     bool ok = !range_err;
     int hmmfrom = 0, hmmto = 0, sqfrom = 0, sqto = 0;
-#define CELL(row, st, k) F[((int64_t)(row) * 3 + (st)) * QW + (((k) - 1) % Q) * 32 + ((k) - 1) / Q]
+#define CELL(row, st, k) Bm[((int64_t)(row) * 3 + (st)) * QW + (((k) - 1) % Q) * 32 + ((k) - 1) / Q]
 #define TT0(k) (__ldg(p.tfb + ms.blk_off * 64 + ((((k) - 1) % Q) * 32 + ((k) - 1) / Q) * 2))
 #define TT1(k) (__ldg(p.tfb + ms.blk_off * 64 + ((((k) - 1) % Q) * 32 + ((k) - 1) / Q) * 2 + 1))
     if (ok) {
@@ -287,7 +300,7 @@ __global__ void __launch_bounds__(BLK_WARPS * 32) envelope2_kernel(DomdefParams 
           const float a = (i > 0) ? t1s * (xo[(int64_t)(i - 1) * X_NX + X_J] + pps[i * 3 + 1]) : -INFINITY, b = t2s * xc[X_E];
           s1 = (a > b) ? ST_J : ST_E;
         } else if (s0 == ST_E) {
-          const float *dpc = F + (int64_t)i * 3 * QW + lane;
+          const float *dpc = Bm + (int64_t)i * 3 * QW + lane;
           float bmv = -INFINITY; int bk = -1, bdk = -1; float bd = -INFINITY;
 #pragma unroll
           for (int q = 0; q < Q; ++q) {
