@@ -54,6 +54,8 @@ struct ModelScalars {
   float   scale_b, scale_w;
   float   evparam[6];
   int32_t ddbound_w;     // lazy-F bound of the Viterbi filter
+  int16_t vit_emax;      // largest Viterbi emission word of the model (>= 0): packed-kernel values stay < 32767 - vit_emax
+  int16_t vit_tbm;       // most negative B->M entry word (<= 0)
   int32_t vq;            // lane-blocked class: cells per lane (2,4,8,16), 0 = model too long for the blocked kernels
   int64_t blk_off;       // offset of the model's lane-blocked tables (in units of 32 lanes x vq cells)
 };
@@ -85,6 +87,10 @@ struct ckm_models {
   uint4    *d_twb = nullptr;      // per model [vq][32] : 8 int16 transitions of cell (q, lane)
   uint32_t *d_rmb = nullptr;      // per model [KPAD][vq/2][32] : two int16 MSV emission gains bias - cost (q = j, vq/2 + j)
   uint32_t *d_rwb = nullptr;      // per model [KPAD][vq/2][32] : two int16 emissions (q = 2j, 2j+1)
+  // packed (int16x2) Viterbi tables: word w of lane l pairs positions k = l*W + w + 1 (low half) and 32*W + k (high half),
+  // W = vq/2, every entry clamped to >= -22528 (kernels_vitp.cu)
+  uint4    *d_twp = nullptr;      // per model [W][32][2] : {BM MM IM DM} {MD MI II DD}, one int16x2 word each
+  uint32_t *d_rwp = nullptr;      // per model [KPAD][W][32]
   float4   *d_tfb = nullptr;      // per model [vq][32][2] : 8 fp32 transitions
   float    *d_rfb = nullptr;      // per model [KPAD][vq][32] : fp32 emission odds
   int64_t   total_cols = 0;

@@ -173,6 +173,12 @@ int models_build_device(ckm_models &db) {
     s.scale_b = m.scale_b; s.scale_w = m.scale_w;
     for (int z = 0; z < 6; ++z) s.evparam[z] = m.evparam[z];
     s.ddbound_w = m.ddbound_w;
+    {
+      int emax = 0, tbm = 0;
+      for (int x = 0; x < KP; ++x) for (int k = 1; k <= m.M; ++k) emax = std::max(emax, (int)m.rwv[(size_t)x * (m.M + 1) + k]);
+      for (int k = 1; k <= m.M; ++k) tbm = std::min(tbm, (int)m.twv[(size_t)k * T_N + 0]);
+      s.vit_emax = (int16_t)emax; s.vit_tbm = (int16_t)tbm;
+    }
     s.vq = (m.M <= 64) ? 2 : (m.M <= 128) ? 4 : (m.M <= 192) ? 6 : (m.M <= 256) ? 8 : (m.M <= 384) ? 12 : (m.M <= 512) ? 16 : (m.M <= 640) ? 20 : (m.M <= 768) ? 24 : (m.M <= 896) ? 28 : (m.M <= 1024) ? 32 : 0;
     s.blk_off = blk_units;
     s.msv2_ok = (s.vq != 0 && (int)m.base_b + (int)m.bias_b < 255) ? 1 : 0;
@@ -205,6 +211,8 @@ int models_build_device(ckm_models &db) {
   std::vector<uint32_t> rwb((size_t)std::max<int64_t>(blk_units, 1) * 32 * KPAD / 2 + 32);
   std::vector<uint32_t> rmb((size_t)std::max<int64_t>(blk_units, 1) * 32 * KPAD / 2 + 32);
   std::vector<float4> tfb((size_t)std::max<int64_t>(blk_units, 1) * 32 * 2);
+  std::vector<uint4> twp((size_t)std::max<int64_t>(blk_units, 1) * 32);              // W = vq/2 words x 32 lanes x 2 uint4
+  std::vector<uint32_t> rwp((size_t)std::max<int64_t>(blk_units, 1) * 32 * KPAD / 2 + 32);
   std::vector<float> rfb((size_t)std::max<int64_t>(blk_units, 1) * 32 * KPAD);
   for (int i = 0; i < n; ++i) {
     const Model &m = db.models[i];
@@ -239,7 +247,34 @@ int models_build_device(ckm_models &db) {
         }
       }
   }
+  // packed Viterbi tables (kernels_vitp.cu): entries clamped at -22528 and values floored at -10240, so no int16 add can wrap
+  for (int i = 0; i < n; ++i) {
+    const Model &m = db.models[i];
+    const ModelScalars &s = sc[i];
+    if (s.vq == 0) continue;
+    const int W = s.vq / 2;
+    const size_t W1 = (size_t)m.M + 1;
+    auto clampw = [](int v) { return (uint32_t)(uint16_t)(int16_t)std::max(v, -22528); };
+    for (int w = 0; w < W; ++w)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int k0 = lane * W + w + 1, k1 = 32 * W + k0;
+        uint32_t tw[8];
+        for (int z = 0; z < 8; ++z) {
+          const int a = (k0 <= m.M) ? (int)m.twv[(size_t)k0 * T_N + z] : -32768, b = (k1 <= m.M) ? (int)m.twv[(size_t)k1 * T_N + z] : -32768;
+          tw[z] = clampw(a) | (clampw(b) << 16);
+        }
+        const size_t base = ((size_t)s.blk_off / 2 * 32 + (size_t)w * 32 + lane) * 2;
+        twp[base] = make_uint4(tw[0], tw[1], tw[2], tw[3]);
+        twp[base + 1] = make_uint4(tw[4], tw[5], tw[6], tw[7]);
+        for (int x = 0; x < KPAD; ++x) {
+          const int a = (k0 <= m.M && x < KP) ? (int)m.rwv[(size_t)x * W1 + k0] : -32768, b = (k1 <= m.M && x < KP) ? (int)m.rwv[(size_t)x * W1 + k1] : -32768;
+          rwp[(size_t)s.blk_off * 32 * KPAD / 2 + ((size_t)x * W + w) * 32 + lane] = clampw(a) | (clampw(b) << 16);
+        }
+      }
+  }
   int st;
+  if ((st = upload(&db.d_twp, twp))) return st;
+  if ((st = upload(&db.d_rwp, rwp))) return st;
   if ((st = upload(&db.d_twb, twb))) return st;
   if ((st = upload(&db.d_rwb, rwb))) return st;
   if ((st = upload(&db.d_rmb, rmb))) return st;
@@ -266,7 +301,7 @@ int models_build_device(ckm_models &db) {
 
 void models_free_device(ckm_models &db) {
   cudaFree(db.d_scalars); cudaFree(db.d_rbv); cudaFree(db.d_rwv); cudaFree(db.d_twv); cudaFree(db.d_rfv); cudaFree(db.d_tfv);
-  cudaFree(db.d_bias_eo); cudaFree(db.d_twb); cudaFree(db.d_rwb); cudaFree(db.d_rmb); cudaFree(db.d_tfb); cudaFree(db.d_rfb); cudaFree(db.d_tile_blob); cudaFree(db.d_tiles); cudaFree(db.d_tile_models); cudaFree(db.d_groups);
+  cudaFree(db.d_bias_eo); cudaFree(db.d_twb); cudaFree(db.d_twp); cudaFree(db.d_rwp); cudaFree(db.d_rwb); cudaFree(db.d_rmb); cudaFree(db.d_tfb); cudaFree(db.d_rfb); cudaFree(db.d_tile_blob); cudaFree(db.d_tiles); cudaFree(db.d_tile_models); cudaFree(db.d_groups);
   cudaFree(db.d_chain_first_tile); cudaFree(db.d_chain_ntiles);
 }
 

@@ -17,9 +17,10 @@ thread_local ckm_engine *g_pool_engine = nullptr;
 thread_local int g_pool_next = 0;
 
 static bool use_blocked_kernels();
+static bool use_packed_viterbi() { const char *v = std::getenv("CKM_VITP"); return use_blocked_kernels() && !(v != nullptr && v[0] == '0'); }
 static int fan_out(ckm_engine *e);
 static int fan_in(ckm_engine *e);
-enum { CTR_UNIT4 = 0, CTR_UNIT8, CTR_UNIT16, CTR_UNIT32, CTR_CAND, CTR_MSV, CTR_BIAS, CTR_VIT, CTR_FWD, CTR_ENV, CTR_DOM, CTR_N = 32 };
+enum { CTR_UNIT4 = 0, CTR_UNIT8, CTR_UNIT16, CTR_UNIT32, CTR_CAND, CTR_MSV, CTR_BIAS, CTR_VIT, CTR_FWD, CTR_ENV, CTR_DOM, CTR_VREDO, CTR_N = 32 };
 
 struct ActiveMasks {
   DevBuf tile_active, model_active, model_slot;
@@ -156,7 +157,7 @@ static int run_stage1(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
 
 // Stages 2-4 on the MSV survivors: bias filter -> ViterbiFilter -> ForwardParser.  Lists ping-pong between two buffers.
 struct Stage2 {
-  DevBuf a, b;
+  DevBuf a, b, redo;
   int32_t cap = 0;
   Candidate *fwd_list = nullptr;      // survivors of the Forward filter (points into a or b)
 };
@@ -168,11 +169,14 @@ static int run_stage2(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
   s2.cap = s1.pass_cap;
   if ((rc = s2.a.alloc(sizeof(Candidate) * (size_t)s2.cap))) return rc;
   if ((rc = s2.b.alloc(sizeof(Candidate) * (size_t)s2.cap))) return rc;
+  if ((rc = s2.redo.alloc(sizeof(Candidate) * (size_t)s2.cap))) return rc;
   const int nsm = e->prop.multiProcessorCount;
   FilterParams p{};
   p.res = db->d_res; p.off = db->d_off; p.len = db->d_len; p.lenA = db->d_lenA; p.lenB = db->d_lenB; p.tmove_w = db->d_tmove_w;
   p.ms = m->d_scalars; p.bias_eo = m->d_bias_eo; p.rwv = m->d_rwv; p.twv = m->d_twv; p.rfv = m->d_rfv; p.tfv = m->d_tfv;
   p.twb = m->d_twb; p.rwb = m->d_rwb; p.tfb = m->d_tfb; p.rfb = m->d_rfb;
+  p.twp = m->d_twp; p.rwp = m->d_rwp;
+  p.redo = s2.redo.as<Candidate>(); p.redo_count = e->d_counters + CTR_VREDO; p.redo_cap = s2.cap;
   p.row_elems = ((m->maxM + 31) / 32) * 32 + 64;
   p.F1 = 0.02; p.F2 = 1e-3; p.F3 = 1e-5;
   p.use_blk = use_blocked_kernels() ? 1 : 0;
@@ -186,6 +190,16 @@ static int run_stage2(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
   // viterbi: a -> b
   p.in = s2.a.as<Candidate>(); p.in_count = e->d_counters + CTR_BIAS; p.in_cap = s2.cap;
   p.out = s2.b.as<Candidate>(); p.out_count = e->d_counters + CTR_VIT; p.out_cap = s2.cap;
+  if (use_packed_viterbi()) {
+    // packed int16x2 kernels, one per class; what they cannot score exactly (strong hits near the int16 ceiling, models
+    // without a class, pairs outside the safety conditions of kernels_vitp.cu) lands in the redo list ...
+    if ((rc = fan_out(e))) return rc;
+    for (int c = 0; c < N_BLK_CLASSES; ++c) if ((rc = launch_vitp(p, c, nsm * 8, e->cls[c]))) return rc;
+    if ((rc = fan_in(e))) return rc;
+    // ... which the int32 kernels below then take as their input
+    p.in = s2.redo.as<Candidate>(); p.in_count = e->d_counters + CTR_VREDO; p.in_cap = s2.cap;
+    e->stats.kernel_launches += N_BLK_CLASSES;
+  }
   if ((rc = fan_out(e))) return rc;
   for (int c = 0; c < N_BLK_CLASSES; ++c) if ((rc = launch_vit2(p, c, nsm * 8, e->cls[c]))) return rc;      // lane-blocked register kernels, one per class
   if ((rc = launch_vit(p, nsm * 4, e->cls[N_BLK_CLASSES]))) return rc;                                      // models beyond the classes: shared-memory rows
@@ -246,7 +260,7 @@ int ckm_filter_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_i
   for (const Candidate &c : pass1) passed_out[(int64_t)slot[c.model] * db->nseq + c.seq] |= 1;
   e->stats.n_pairs = n;
   e->stats.n_ssv_cand = ctr[CTR_CAND]; e->stats.n_past_msv = ctr[CTR_MSV]; e->stats.n_past_bias = ctr[CTR_BIAS];
-  e->stats.n_past_vit = ctr[CTR_VIT]; e->stats.n_past_fwd = ctr[CTR_FWD];
+  e->stats.n_past_vit = ctr[CTR_VIT]; e->stats.n_past_fwd = ctr[CTR_FWD]; e->stats.n_vit_redo = ctr[CTR_VREDO];
   cudaEventElapsedTime(&e->stats.ms_ssv, e->ev[0], e->ev[1]);
   cudaEventElapsedTime(&e->stats.ms_msv, e->ev[1], e->ev[2]);
   cudaEventElapsedTime(&e->stats.ms_bias, e->ev[2], e->ev[3]);
@@ -337,7 +351,7 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
   }
   e->stats.n_pairs = n_pairs; e->stats.n_cells = (int64_t)cells;
   e->stats.n_ssv_cand = ctr[CTR_CAND]; e->stats.n_past_msv = ctr[CTR_MSV]; e->stats.n_past_bias = ctr[CTR_BIAS];
-  e->stats.n_past_vit = ctr[CTR_VIT]; e->stats.n_past_fwd = ctr[CTR_FWD];
+  e->stats.n_past_vit = ctr[CTR_VIT]; e->stats.n_past_fwd = ctr[CTR_FWD]; e->stats.n_vit_redo = ctr[CTR_VREDO];
   const int npairs = ctr[CTR_FWD];
   std::vector<Candidate> fl((size_t)npairs);
   if (npairs) CKM_CUDA(cudaMemcpy(fl.data(), s2.fwd_list, sizeof(Candidate) * fl.size(), cudaMemcpyDeviceToHost));

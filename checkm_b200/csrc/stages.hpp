@@ -55,6 +55,8 @@ struct FilterParams {
   const ModelScalars *ms;
   const float *bias_eo; const int16_t *rwv; const int16_t *twv; const float *rfv; const float *tfv;
   const uint4 *twb; const uint32_t *rwb; const float4 *tfb; const float *rfb;   // lane-blocked tables
+  const uint4 *twp; const uint32_t *rwp;                                         // packed Viterbi tables
+  Candidate *redo; int32_t *redo_count; int32_t redo_cap;                       // pairs the packed Viterbi kernel hands to the int32 kernels
   const Candidate *in; const int32_t *in_count; int32_t in_cap;
   Candidate *out; int32_t *out_count; int32_t out_cap;
   int32_t row_elems;                 // shared-memory elements of one DP row
@@ -70,6 +72,7 @@ int launch_vit(const FilterParams &p, int grid, cudaStream_t st);
 constexpr int N_BLK_CLASSES = 10;
 constexpr int BLK_Q[N_BLK_CLASSES] = {2, 4, 6, 8, 12, 16, 20, 24, 28, 32};
 int launch_vit2(const FilterParams &p, int cls, int grid, cudaStream_t st);
+int launch_vitp(const FilterParams &p, int cls, int grid, cudaStream_t st);   // packed int16x2 kernels (kernels_vitp.cu)
 int launch_fwd(const FilterParams &p, int grid, cudaStream_t st);
 
 // ---- stage 5: domain definition ----

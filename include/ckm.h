@@ -80,6 +80,7 @@ typedef struct {
   int64_t n_reported;     /* domtblout rows                                   */
   float   ms_ssv, ms_msv, ms_bias, ms_vit, ms_fwd, ms_domdef, ms_total;   /* CUDA-event times of the last search */
   int64_t kernel_launches;
+  int64_t n_vit_redo;     /* pairs the packed Viterbi kernel handed to the int32 kernel (strong hits, guard conditions) */
 } ckm_stats;
 
 /* ---- per-bin QA row = the integers/floats behind CheckM's table
