@@ -46,6 +46,7 @@ int ckm_init(int device, ckm_engine **out) {
   int prio_lo = 0, prio_hi = 0;
   CKM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   for (auto &s : eng->cls) CKM_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_hi));
+  CKM_CUDA(cudaStreamCreateWithPriority(&eng->aux, cudaStreamNonBlocking, prio_hi));
   for (auto &ev : eng->cls_ev) CKM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CKM_CUDA(cudaEventCreateWithFlags(&eng->fan_ev, cudaEventDisableTiming));
   CKM_CUDA(cudaMalloc((void **)&eng->d_counters, 64 * sizeof(int32_t) + 64));
@@ -65,6 +66,7 @@ void ckm_destroy(ckm_engine *e) {
   cudaStreamSynchronize(e->stream);
   for (auto &ev : e->ev) cudaEventDestroy(ev);
   for (auto &s : e->cls) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+  if (e->aux) { cudaStreamSynchronize(e->aux); cudaStreamDestroy(e->aux); }
   for (auto &ev : e->cls_ev) cudaEventDestroy(ev);
   cudaEventDestroy(e->fan_ev);
   cudaFree(e->d_counters);

@@ -145,6 +145,7 @@ struct ckm_engine {
   static constexpr int NCLS = 11;
   cudaStream_t cls[NCLS];
   cudaEvent_t cls_ev[NCLS], fan_ev;
+  cudaStream_t aux = nullptr;     // the trace-ensemble job of a search runs here, next to the class streams
   ckm_stats stats;
   // grow-only device buffer cache: slot -> (pointer, bytes); search/reduce workspaces are reused across calls
   std::vector<std::pair<void *, size_t>> pool;

@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(BLK_WARPS * 32) envelope2_kernel(DomdefParams 
       out.envsc = envsc; out.oasc = oasc; out.domcorrection = domcorrection;
       out.hmmfrom = hmmfrom; out.hmmto = hmmto; out.sqfrom = sqfrom; out.sqto = sqto;
       out.bitscore = 0.f; out.dombias = 0.f; out.pad = 0.f; out.lnP = 0.0;
-      p.doms[ei] = out;
+      p.doms[env.slot] = out;
     }
     __syncwarp();
   }

@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) envelope_kernel(DomdefParams p
       out.ok = ok ? 1 : 0;
       out.envsc = envsc; out.oasc = oasc; out.domcorrection = domcorrection;
       out.hmmfrom = hmmfrom; out.hmmto = hmmto; out.sqfrom = sqfrom; out.sqto = sqto;
-      p.doms[ei] = out;
+      p.doms[env.slot] = out;
     }
     __syncwarp();
   }

@@ -14,7 +14,7 @@ namespace ckm {
 
 constexpr int NSAMPLES = 200;
 constexpr int SPCAP = 4096;           // sampled segments kept per region
-constexpr int MAXENV = 32;            // envelopes reported per region
+constexpr int MAXENV = ENS_MAXENV;    // envelopes reported per region
 
 struct EnsembleParams {
   DomdefParams d;
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) ensemble_kernel(EnsembleParams
         for (int h = 0; h < nsp; ++h) if (assign[h] == c) epc[spb[h * 5 + 2] - jmin]++;
         for (cmv = 0, best_j = jmax; best_j >= jmin; --best_j) { cmv += epc[best_j - jmin]; if ((float)cmv / (float)ninc >= 0.02f) break; }
         if (best_i > best_j) continue;
-        if (nout < MAXENV) { eo[nout].pair = reg.pair; eo[nout].i = best_i; eo[nout].j = best_j; eo[nout].null2_done = 1; eo[nout].scratch_off = 0; nout++; }
+        if (nout < MAXENV) { eo[nout].pair = reg.pair; eo[nout].i = best_i; eo[nout].j = best_j; eo[nout].null2_done = 1; eo[nout].scratch_off = 0; eo[nout].slot = 0; eo[nout].pad = 0; nout++; }
       }
       // order of occurrence in the target
       for (int a = 1; a < nout; ++a) { Envelope v = eo[a]; int b = a - 1; while (b >= 0 && eo[b].i > v.i) { eo[b + 1] = eo[b]; --b; } eo[b + 1] = v; }
@@ -386,47 +386,63 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) ensemble_kernel(EnsembleParams
   }
 }
 
-int run_ensembles(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, DomdefParams &p, const std::vector<PairWork> &pairs,
-                  const std::vector<Region> &regs, const std::vector<int> &multi_idx, std::vector<std::vector<Envelope>> &out) {
-  (void)db;
-  cudaStream_t st = e->stream;
-  const int nm = (int)multi_idx.size();
-  std::vector<int64_t> off(nm);
+// The ensemble of all multi-domain regions as an asynchronous job on stream `st`: ensembles_launch enqueues the uploads,
+// the kernel and the downloads; ensembles_collect waits for them and hands back the envelopes of every region.
+struct EnsembleJob {
+  DevBuf b_regs, b_idx, b_off, b_scr, b_env, b_cnt;       // workspaces from the engine's cache (the caller holds the PoolScope)
+  std::vector<int64_t> off;
+  std::vector<Envelope> envs;
+  std::vector<int32_t> cnt;
+  int nm = 0;
+};
+
+int ensembles_launch(ckm_engine *e, const ckm_models *m, DomdefParams &p, const std::vector<PairWork> &pairs,
+                     const std::vector<Region> &regs, const std::vector<int> &multi_idx, cudaStream_t st, EnsembleJob **job_out) {
+  EnsembleJob *job = new EnsembleJob();
+  *job_out = job;
+  const int nm = job->nm = (int)multi_idx.size();
+  job->off.resize(nm);
   int64_t tot = 0;
   for (int i = 0; i < nm; ++i) {
     const Region &r = regs[multi_idx[i]];
     const int64_t Lr = r.j - r.i + 1, M = m->models[pairs[r.pair].model].M, Mpad = ((M + 1) + 31) / 32 * 32 + 32;
-    off[i] = tot;
+    job->off[i] = tot;
     tot += (Lr + 1) * 3 * Mpad + (Lr + 1) * X_NX + 2 * (Lr + 1) + (int64_t)SPCAP * 8 + std::max(Lr, M) + 2 + 256 + 64;
     tot = (tot + 63) / 64 * 64;
   }
-  DevBuf b_regs, b_idx, b_off, b_scr, b_env, b_cnt;       // workspaces from the engine's cache (the caller holds the PoolScope)
   int rc;
-  if ((rc = b_regs.alloc(sizeof(Region) * regs.size())) || (rc = b_idx.alloc(sizeof(int32_t) * nm)) || (rc = b_off.alloc(sizeof(int64_t) * nm)) ||
-      (rc = b_scr.alloc(sizeof(float) * (size_t)tot)) || (rc = b_env.alloc(sizeof(Envelope) * (size_t)nm * MAXENV)) || (rc = b_cnt.alloc(sizeof(int32_t) * nm))) return rc;
-  void *d_regs = b_regs.p, *d_idx = b_idx.p, *d_off = b_off.p, *d_scr = b_scr.p, *d_env = b_env.p, *d_cnt = b_cnt.p;
-#define ENS_CUDA(call) CKM_CUDA(call)
-  ENS_CUDA(cudaMemcpyAsync(d_regs, regs.data(), sizeof(Region) * regs.size(), cudaMemcpyHostToDevice, st));
-  ENS_CUDA(cudaMemcpyAsync(d_idx, multi_idx.data(), sizeof(int32_t) * nm, cudaMemcpyHostToDevice, st));
-  ENS_CUDA(cudaMemcpyAsync(d_off, off.data(), sizeof(int64_t) * nm, cudaMemcpyHostToDevice, st));
-  ENS_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int32_t) * nm, st));
+  if ((rc = job->b_regs.alloc(sizeof(Region) * regs.size())) || (rc = job->b_idx.alloc(sizeof(int32_t) * nm)) || (rc = job->b_off.alloc(sizeof(int64_t) * nm)) ||
+      (rc = job->b_scr.alloc(sizeof(float) * (size_t)tot)) || (rc = job->b_env.alloc(sizeof(Envelope) * (size_t)nm * MAXENV)) || (rc = job->b_cnt.alloc(sizeof(int32_t) * nm))) return rc;
+  CKM_CUDA(cudaMemcpyAsync(job->b_regs.p, regs.data(), sizeof(Region) * regs.size(), cudaMemcpyHostToDevice, st));       // regs, multi_idx outlive the job (caller)
+  CKM_CUDA(cudaMemcpyAsync(job->b_idx.p, multi_idx.data(), sizeof(int32_t) * nm, cudaMemcpyHostToDevice, st));
+  CKM_CUDA(cudaMemcpyAsync(job->b_off.p, job->off.data(), sizeof(int64_t) * nm, cudaMemcpyHostToDevice, st));
+  CKM_CUDA(cudaMemsetAsync(job->b_cnt.p, 0, sizeof(int32_t) * nm, st));
   EnsembleParams ep;
-  ep.d = p; ep.regions = (const Region *)d_regs; ep.multi_idx = (const int32_t *)d_idx; ep.nmulti = nm;
-  ep.scratch_off = (const int64_t *)d_off; ep.scratch = (float *)d_scr; ep.env_out = (Envelope *)d_env; ep.env_count = (int32_t *)d_cnt;
+  ep.d = p; ep.regions = job->b_regs.as<Region>(); ep.multi_idx = job->b_idx.as<int32_t>(); ep.nmulti = nm;
+  ep.scratch_off = job->b_off.as<int64_t>(); ep.scratch = job->b_scr.as<float>(); ep.env_out = job->b_env.as<Envelope>(); ep.env_count = job->b_cnt.as<int32_t>();
   const size_t smem = (size_t)FWD_WARPS * 3 * p.row_elems * sizeof(float);
-  ENS_CUDA(cudaFuncSetAttribute(ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CKM_CUDA(cudaFuncSetAttribute(ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(e->prop.multiProcessorCount * 4, (nm + FWD_WARPS - 1) / FWD_WARPS);
   ensemble_kernel<<<grid, FWD_WARPS * 32, smem, st>>>(ep);
-  ENS_CUDA(cudaGetLastError());
+  CKM_CUDA(cudaGetLastError());
   e->stats.kernel_launches++;
-  std::vector<Envelope> envs((size_t)nm * MAXENV);
-  std::vector<int32_t> cnt(nm);
-  ENS_CUDA(cudaMemcpyAsync(envs.data(), d_env, sizeof(Envelope) * envs.size(), cudaMemcpyDeviceToHost, st));
-  ENS_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(int32_t) * nm, cudaMemcpyDeviceToHost, st));
-  ENS_CUDA(cudaStreamSynchronize(st));
-  for (int i = 0; i < nm; ++i)
-    for (int c = 0; c < cnt[i]; ++c) out[i].push_back(envs[(size_t)i * MAXENV + c]);
+  job->envs.resize((size_t)nm * MAXENV);
+  job->cnt.resize(nm);
+  CKM_CUDA(cudaMemcpyAsync(job->envs.data(), job->b_env.p, sizeof(Envelope) * job->envs.size(), cudaMemcpyDeviceToHost, st));
+  CKM_CUDA(cudaMemcpyAsync(job->cnt.data(), job->b_cnt.p, sizeof(int32_t) * nm, cudaMemcpyDeviceToHost, st));
   return CKM_OK;
 }
+
+int ensembles_collect(EnsembleJob *job, cudaStream_t st, std::vector<std::vector<Envelope>> &out) {
+  cudaError_t err = cudaStreamSynchronize(st);
+  if (err == cudaSuccess) {
+    out.assign((size_t)job->nm, {});
+    for (int i = 0; i < job->nm; ++i)
+      for (int c = 0; c < job->cnt[i] && c < MAXENV; ++c) out[i].push_back(job->envs[(size_t)i * MAXENV + c]);
+  }
+  delete job;
+  return err == cudaSuccess ? CKM_OK : cuda_fail(err, "ensemble job");
+}
+void ensembles_abandon(EnsembleJob *job, cudaStream_t st) { if (job) { cudaStreamSynchronize(st); delete job; } }
 
 }  // namespace ckm

@@ -274,8 +274,11 @@ int ckm_filter_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_i
 namespace ckm {
 
 constexpr int X_NX_HOST = 6;
-int run_ensembles(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, DomdefParams &p, const std::vector<PairWork> &pairs,
-                  const std::vector<Region> &regs, const std::vector<int> &multi_idx, std::vector<std::vector<Envelope>> &out);
+struct EnsembleJob;
+int ensembles_launch(ckm_engine *e, const ckm_models *m, DomdefParams &p, const std::vector<PairWork> &pairs,
+                     const std::vector<Region> &regs, const std::vector<int> &multi_idx, cudaStream_t st, EnsembleJob **job_out);
+int ensembles_collect(EnsembleJob *job, cudaStream_t st, std::vector<std::vector<Envelope>> &out);
+void ensembles_abandon(EnsembleJob *job, cudaStream_t st);
 
 static bool use_blocked_kernels() { const char *v = std::getenv("CKM_BLK"); return !(v != nullptr && v[0] == '0'); }
 static int vq_of(int M) { return (M <= 64) ? 2 : (M <= 128) ? 4 : (M <= 192) ? 6 : (M <= 256) ? 8 : (M <= 384) ? 12 : (M <= 512) ? 16 : (M <= 640) ? 20 : (M <= 768) ? 24 : (M <= 896) ? 28 : (M <= 1024) ? 32 : 0; }
@@ -420,76 +423,107 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
     std::vector<Region> regs((size_t)nreg);
     if (nreg) CKM_CUDA(cudaMemcpy(regs.data(), dregions.p, sizeof(Region) * regs.size(), cudaMemcpyDeviceToHost));
     std::sort(regs.begin(), regs.end(), [](const Region &a, const Region &b) { return a.pair != b.pair ? a.pair < b.pair : a.i < b.i; });
-    // multi-domain regions are resolved by the stochastic-trace ensemble (run_ensembles), which appends envelopes
-    std::vector<Envelope> extra;
+    // Domain slots.  Regions are sorted by (pair, start), so a pair's slots are contiguous and in sequence order: one slot
+    // per single-domain region, ENS_MAXENV per multi-domain region (the ensemble decides how many it fills; unused slots
+    // keep ok = 0 and are skipped by every consumer).  Fixing the slots before the ensemble has run lets the envelopes of
+    // the single-domain regions be rescored WHILE the trace ensemble of the multi-domain ones is still sampling.
     std::vector<int> multi_idx;
-    for (int r = 0; r < nreg; ++r) if (regs[r].multi) multi_idx.push_back(r);
-    std::vector<std::vector<Envelope>> multi_envs(multi_idx.size());
-    if (!multi_idx.empty()) {
-      if ((rc = run_ensembles(e, m, db, p, pairs, regs, multi_idx, multi_envs))) return rc;
-    }
-    size_t mi = 0;
+    std::vector<int32_t> reg_slot((size_t)nreg);
+    int32_t nslots = 0;
     for (int r = 0; r < nreg; ++r) {
-      if (!regs[r].multi) { envs.push_back(Envelope{regs[r].pair, regs[r].i, regs[r].j, 0, 0}); }
-      else { for (const Envelope &en : multi_envs[mi]) envs.push_back(en); ++mi; }
+      PairWork &pw = pairs[regs[r].pair];
+      if (pw.ndom_slots == 0) pw.first_dom = nslots;
+      reg_slot[r] = nslots;
+      const int k = regs[r].multi ? ENS_MAXENV : 1;
+      nslots += k; pw.ndom_slots += k;
+      if (regs[r].multi) multi_idx.push_back(r);
     }
-    // domain slots per pair
-    for (size_t i = 0; i < envs.size(); ++i) {
-      PairWork &pw = pairs[envs[i].pair];
-      if (pw.ndom_slots == 0) pw.first_dom = (int32_t)i;
-      pw.ndom_slots++;
-    }
-    doms.resize(envs.size());
-    if (!envs.empty()) {
-      // scratch per envelope: 2 matrices + specials; run in waves under a memory budget
-      std::vector<int64_t> need(envs.size());
-      for (size_t i = 0; i < envs.size(); ++i) {
-        const PairWork &pw = pairs[envs[i].pair];
-        const int64_t Ld = envs[i].j - envs[i].i + 1, Mpad = ((m->models[pw.model].M + 1) + 31) / 32 * 32 + 32;
-        const int64_t vq = p.use_blk ? vq_of(m->models[pw.model].M) : 0;
-        const int64_t width = vq ? 32 * vq : Mpad;
-        need[i] = 2 * (Ld + 1) * 3 * width + (Ld + 1) * 15 + 64;
-      }
+    doms.assign((size_t)nslots, DomainOut{});
+    std::vector<Envelope> envs1, envs2;
+    for (int r = 0; r < nreg; ++r)
+      if (!regs[r].multi) { Envelope en{}; en.pair = regs[r].pair; en.i = regs[r].i; en.j = regs[r].j; en.slot = reg_slot[r]; envs1.push_back(en); }
+    DevBuf denvs2, deorder2;
+    if (nslots > 0) {
+      if ((rc = ddoms.alloc(sizeof(DomainOut) * (size_t)nslots)) || (rc = dhits.alloc(sizeof(HitOut) * pairs.size()))) return rc;
+      CKM_CUDA(cudaMemsetAsync(ddoms.p, 0, sizeof(DomainOut) * (size_t)nslots, st));
+      CKM_CUDA(cudaMemcpyAsync(dpairs.p, pairs.data(), sizeof(PairWork) * pairs.size(), cudaMemcpyHostToDevice, st));
+      p.doms = ddoms.as<DomainOut>();
       size_t free_b = 0, total_b = 0;
       cudaMemGetInfo(&free_b, &total_b);
-      // fixed scratch budget (the cached pool is reused by every later search): 1/3 of the device, at most 56 GiB
       (void)free_b;
-      int64_t budget = (int64_t)std::min<size_t>(total_b / 3, (size_t)56 << 30) / (int64_t)sizeof(float);
-      budget = std::max<int64_t>(budget, *std::max_element(need.begin(), need.end()));
-      if ((rc = denvs.alloc(sizeof(Envelope) * envs.size())) || (rc = ddoms.alloc(sizeof(DomainOut) * envs.size())) || (rc = dhits.alloc(sizeof(HitOut) * pairs.size()))) return rc;
-      CKM_CUDA(cudaMemcpyAsync(dpairs.p, pairs.data(), sizeof(PairWork) * pairs.size(), cudaMemcpyHostToDevice, st));
-      std::vector<int8_t> ecls(envs.size());
-      for (size_t i = 0; i < envs.size(); ++i) ecls[i] = (int8_t)cls_of(m->models[pairs[envs[i].pair].model].M, p.use_blk != 0);
-      if ((rc = deorder.alloc(sizeof(int32_t) * envs.size()))) return rc;
-      std::vector<int32_t> eorder(envs.size());
-      size_t w0 = 0;
+      // fixed scratch budget (the cached pool is reused by every later search): 1/3 of the device, at most 56 GiB
+      const int64_t budget0 = (int64_t)std::min<size_t>(total_b / 3, (size_t)56 << 30) / (int64_t)sizeof(float);
       int64_t cur_alloc = 0;
-      while (w0 < envs.size()) {
-        size_t w1 = w0; int64_t tot = 0;
-        while (w1 < envs.size() && (w1 == w0 || tot + need[w1] <= budget)) { envs[w1].scratch_off = tot; tot += need[w1]; ++w1; }
-        if (tot > cur_alloc) { if ((rc = dscratch.alloc(sizeof(float) * (size_t)tot))) return rc; cur_alloc = tot; }
-        // this wave's envelopes grouped by class, largest first; one stream per class
-        for (size_t i = w0; i < w1; ++i) eorder[i] = (int32_t)i;
-        std::stable_sort(eorder.begin() + w0, eorder.begin() + w1, [&](int32_t a, int32_t b) { return ecls[a] != ecls[b] ? ecls[a] < ecls[b] : need[a] > need[b]; });
-        CKM_CUDA(cudaMemcpyAsync(denvs.as<Envelope>() + w0, envs.data() + w0, sizeof(Envelope) * (w1 - w0), cudaMemcpyHostToDevice, st));
-        CKM_CUDA(cudaMemcpyAsync(deorder.as<int32_t>() + w0, eorder.data() + w0, sizeof(int32_t) * (w1 - w0), cudaMemcpyHostToDevice, st));
-        p.envs = denvs.as<Envelope>(); p.env_order = deorder.as<int32_t>(); p.scratch = dscratch.as<float>(); p.doms = ddoms.as<DomainOut>();
-        if ((rc = fan_out(e))) return rc;
-        size_t b0 = w0;
-        while (b0 < w1) {
-          size_t b1 = b0; const int c = ecls[eorder[b0]];
-          while (b1 < w1 && ecls[eorder[b1]] == c) ++b1;
-          p.env_begin = (int32_t)b0; p.env_end = (int32_t)b1;
-          const int cnt = (int)(b1 - b0);
-          if (c < N_BLK_CLASSES) rc = launch_envelopes2(p, c, std::min<int>(nsm * 8, (cnt + 3) / 4), e->cls[c]);
-          else rc = launch_envelopes(p, std::min<int>(nsm * 4, (cnt + FWD_WARPS - 1) / FWD_WARPS), e->cls[c]);
-          if (rc) return rc;
-          e->stats.kernel_launches++;
-          b0 = b1;
+      // Rescores a batch of envelopes: 2 matrices + specials of scratch each, in waves under the budget, every class on its
+      // own stream.  leave_last: the last wave is left running on the class streams (the caller joins them with fan_in).
+      auto run_env_batch = [&](std::vector<Envelope> &ev, DevBuf &d_ev, DevBuf &d_ord, bool leave_last) -> int {
+        if (ev.empty()) return CKM_OK;
+        int rc2;
+        std::vector<int64_t> need(ev.size());
+        std::vector<int8_t> ecls(ev.size());
+        for (size_t i = 0; i < ev.size(); ++i) {
+          const PairWork &pw = pairs[ev[i].pair];
+          const int64_t Ld = ev[i].j - ev[i].i + 1, Mpad = ((m->models[pw.model].M + 1) + 31) / 32 * 32 + 32;
+          const int64_t vq = p.use_blk ? vq_of(m->models[pw.model].M) : 0;
+          const int64_t width = vq ? 32 * vq : Mpad;
+          need[i] = 2 * (Ld + 1) * 3 * width + (Ld + 1) * 15 + 64;
+          ecls[i] = (int8_t)cls_of(m->models[pw.model].M, p.use_blk != 0);
         }
-        if ((rc = fan_in(e))) return rc;
-        CKM_CUDA(cudaStreamSynchronize(st));
-        w0 = w1;
+        const int64_t budget = std::max<int64_t>(budget0, *std::max_element(need.begin(), need.end()));
+        if ((rc2 = d_ev.alloc(sizeof(Envelope) * ev.size())) || (rc2 = d_ord.alloc(sizeof(int32_t) * ev.size()))) return rc2;
+        std::vector<int32_t> eorder(ev.size());
+        size_t w0 = 0;
+        while (w0 < ev.size()) {
+          size_t w1 = w0; int64_t tot = 0;
+          while (w1 < ev.size() && (w1 == w0 || tot + need[w1] <= budget)) { ev[w1].scratch_off = tot; tot += need[w1]; ++w1; }
+          if (tot > cur_alloc) { if ((rc2 = dscratch.alloc(sizeof(float) * (size_t)tot))) return rc2; cur_alloc = tot; }
+          // this wave's envelopes grouped by class, largest first; one stream per class
+          for (size_t i = w0; i < w1; ++i) eorder[i] = (int32_t)i;
+          std::stable_sort(eorder.begin() + w0, eorder.begin() + w1, [&](int32_t a, int32_t b) { return ecls[a] != ecls[b] ? ecls[a] < ecls[b] : need[a] > need[b]; });
+          CKM_CUDA(cudaMemcpyAsync(d_ev.as<Envelope>() + w0, ev.data() + w0, sizeof(Envelope) * (w1 - w0), cudaMemcpyHostToDevice, st));
+          CKM_CUDA(cudaMemcpyAsync(d_ord.as<int32_t>() + w0, eorder.data() + w0, sizeof(int32_t) * (w1 - w0), cudaMemcpyHostToDevice, st));
+          p.envs = d_ev.as<Envelope>(); p.env_order = d_ord.as<int32_t>(); p.scratch = dscratch.as<float>();
+          if ((rc2 = fan_out(e))) return rc2;
+          size_t b0 = w0;
+          while (b0 < w1) {
+            size_t b1 = b0; const int c = ecls[eorder[b0]];
+            while (b1 < w1 && ecls[eorder[b1]] == c) ++b1;
+            p.env_begin = (int32_t)b0; p.env_end = (int32_t)b1;
+            const int cnt = (int)(b1 - b0);
+            if (c < N_BLK_CLASSES) rc2 = launch_envelopes2(p, c, std::min<int>(nsm * 8, (cnt + 3) / 4), e->cls[c]);
+            else rc2 = launch_envelopes(p, std::min<int>(nsm * 4, (cnt + FWD_WARPS - 1) / FWD_WARPS), e->cls[c]);
+            if (rc2) return rc2;
+            e->stats.kernel_launches++;
+            b0 = b1;
+          }
+          CKM_CUDA(cudaStreamSynchronize(st));          // the two copies above have read the host vectors
+          if (w1 < ev.size() || !leave_last) {
+            if ((rc2 = fan_in(e))) return rc2;
+            CKM_CUDA(cudaStreamSynchronize(st));
+          }
+          w0 = w1;
+        }
+        return CKM_OK;
+      };
+      // The envelope kernels of the single-domain regions go first (class streams); the trace ensemble of the multi-domain
+      // regions (one warp per region, latency-bound) is queued on its own stream and takes the SMs as they drain.  (Started
+      // the other way round the two compete for the memory system and the ensemble's dependent loads take 2-3x longer.)
+      EnsembleJob *job = nullptr;
+      if ((rc = run_env_batch(envs1, denvs, deorder, !multi_idx.empty()))) return rc;
+      if (!multi_idx.empty()) {
+        CKM_CUDA(cudaEventRecord(e->fan_ev, st));
+        CKM_CUDA(cudaStreamWaitEvent(e->aux, e->fan_ev, 0));
+        if ((rc = ensembles_launch(e, m, p, pairs, regs, multi_idx, e->aux, &job))) { ensembles_abandon(job, e->aux); return rc; }
+        if (!envs1.empty()) { if ((rc = fan_in(e))) { ensembles_abandon(job, e->aux); return rc; } CKM_CUDA(cudaStreamSynchronize(st)); }
+      }
+      if (job != nullptr) {
+        std::vector<std::vector<Envelope>> multi_envs;
+        if ((rc = ensembles_collect(job, e->aux, multi_envs))) return rc;
+        for (size_t mi = 0; mi < multi_idx.size(); ++mi) {
+          int c = 0;
+          for (Envelope en : multi_envs[mi]) { if (c >= ENS_MAXENV) break; en.slot = reg_slot[multi_idx[mi]] + c++; envs2.push_back(en); }
+        }
+        if ((rc = run_env_batch(envs2, denvs2, deorder2, false))) return rc;
       }
       p.hits = dhits.as<HitOut>();
       if ((rc = launch_scores(p, (npairs + 127) / 128, st))) return rc;

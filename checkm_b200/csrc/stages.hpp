@@ -84,7 +84,8 @@ struct PairWork {          // one pair that passed the Forward filter
   int64_t row_off;                   // offset (in rows of L+1) of its per-residue arrays
 };
 struct Region { int32_t pair, i, j, multi; };
-struct Envelope { int32_t pair, i, j, null2_done; int64_t scratch_off; };
+constexpr int ENS_MAXENV = 32;      // envelopes (= domain slots) a multi-domain region can yield
+struct Envelope { int32_t pair, i, j, null2_done; int64_t scratch_off; int32_t slot, pad; };   // slot: index of its DomainOut
 struct DomainOut {
   int32_t pair, ienv, jenv, hmmfrom, hmmto, sqfrom, sqto, ok;
   float   envsc, domcorrection, oasc, bitscore, dombias, pad;
