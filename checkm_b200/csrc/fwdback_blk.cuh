@@ -15,11 +15,11 @@ template <int Q, bool TSMEM>
 struct BlkModel {
   int M;
   const float *rfb;            // emissions [KPAD][Q][32] (+ lane already added)
-  const float4 *tsm;           // TSMEM: warp's shared-memory copy [Q][32][2]
+  const float4 *tsm;           // TSMEM: warp's shared-memory copy [2][Q][32] (T0 plane, T1 plane: 16-byte lane stride, conflict-free LDS.128)
   float4 t0[TSMEM ? 1 : Q], t1[TSMEM ? 1 : Q];
   int lane;
-  __device__ __forceinline__ float4 T0(int q) const { return TSMEM ? tsm[(q * 32 + lane) * 2] : t0[TSMEM ? 0 : q]; }       // BM MM IM DM
-  __device__ __forceinline__ float4 T1(int q) const { return TSMEM ? tsm[(q * 32 + lane) * 2 + 1] : t1[TSMEM ? 0 : q]; }   // MD MI II DD
+  __device__ __forceinline__ float4 T0(int q) const { return TSMEM ? tsm[q * 32 + lane] : t0[TSMEM ? 0 : q]; }             // BM MM IM DM
+  __device__ __forceinline__ float4 T1(int q) const { return TSMEM ? tsm[(Q + q) * 32 + lane] : t1[TSMEM ? 0 : q]; }       // MD MI II DD
 };
 
 template <int Q, bool TSMEM>
@@ -31,7 +31,7 @@ __device__ __forceinline__ void blk_model_load(BlkModel<Q, TSMEM> &bm, const Mod
   const float4 *src = tfb + ms.blk_off * 32 * 2;
   if (TSMEM) {
     __syncwarp();
-    for (int q = 0; q < Q; ++q) { tsm[(q * 32 + lane) * 2] = __ldg(src + (q * 32 + lane) * 2); tsm[(q * 32 + lane) * 2 + 1] = __ldg(src + (q * 32 + lane) * 2 + 1); }
+    for (int q = 0; q < Q; ++q) { tsm[q * 32 + lane] = __ldg(src + (q * 32 + lane) * 2); tsm[(Q + q) * 32 + lane] = __ldg(src + (q * 32 + lane) * 2 + 1); }
     __syncwarp();
   } else {
 #pragma unroll

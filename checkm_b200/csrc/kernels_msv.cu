@@ -312,48 +312,76 @@ __global__ void __launch_bounds__(128) msv2_kernel(MsvParams p) {
     bool overflow = false;
     const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + p.off[s]);
     const int nblk = (L + 15) >> 4;
+    // One row: sv <- max(max(shifted sv, xB) + gain, 0); returns the packed row maximum.
+    auto row = [&](const uint32_t (&e)[H], uint32_t XBw) -> uint32_t {
+      uint32_t up = __shfl_up_sync(0xffffffffu, sv[H - 1], 1);
+      if (lane == 0) up = 0u;
+      const uint32_t in0 = __byte_perm(up, sv[H - 1], 0x5432);     // lo: position below my block, hi: my position Q/2
+#pragma unroll
+      for (int j = H - 1; j >= 1; --j) sv[j] = __viaddmax_s16x2(__vmaxs2(sv[j - 1], XBw), e[j], 0u);
+      sv[0] = __viaddmax_s16x2(__vmaxs2(in0, XBw), e[0], 0u);
+      uint32_t xEv = sv[0];
+      if (H == 1) { }
+      else if (H & 1) {
+#pragma unroll
+        for (int j = 1; j + 1 < H; j += 2) xEv = __vimax3_s16x2(xEv, sv[j], sv[j + 1]);
+      } else {
+        xEv = __vmaxs2(xEv, sv[1]);
+#pragma unroll
+        for (int j = 2; j + 1 < H; j += 2) xEv = __vimax3_s16x2(xEv, sv[j], sv[j + 1]);
+      }
+      return xEv;
+    };
+    // Rows go in groups of four with xB held fixed and ONE warp reduction per group: xB = max(base, xJ) - tjbm moves only
+    // when some row's xE - tec exceeds max(base, xJ), and while it does not, xJ after the group is max(xJ, group max - tec)
+    // -- exactly what the row-by-row recurrence gives.  A group whose maximum could move xB (or overflow) is replayed row by
+    // row from the saved registers; that happens only around the few high-scoring rows of a pair.
+    uint4 r16 = (nblk > 0) ? __ldg(rp) : make_uint4(0, 0, 0, 0);
     for (int b = 0; b < nblk && !overflow; ++b) {
-      const uint4 r16 = __ldg(rp + b);
-      const uint32_t w4[4] = {r16.x, r16.y, r16.z, r16.w};
-      const int rows = min(16, L - b * 16);
-      uint32_t e[H], en[H];
-      {
-        const uint32_t x0 = w4[0] & 0xffu;
+      const uint4 rnext = (b + 1 < nblk) ? __ldg(rp + b + 1) : make_uint4(0, 0, 0, 0);
+      for (int j4 = 0; j4 < 4 && !overflow; ++j4) {
+        const int i0 = b * 16 + j4 * 4;
+        if (i0 >= L) break;
+        const uint32_t wcur = (j4 == 0) ? r16.x : (j4 == 1) ? r16.y : (j4 == 2) ? r16.z : r16.w;
+        const int nrow = min(4, L - i0);
+        uint32_t eg[4][H];
 #pragma unroll
-        for (int j = 0; j < H; ++j) en[j] = __ldg(rmb + (x0 * H + j) * 32);
-      }
-      for (int r = 0; r < rows; ++r) {
+        for (int rr = 0; rr < 4; ++rr) {
+          const uint32_t x = (wcur >> (8 * rr)) & 0xffu;       // rows past L read the padding code: a valid table row, never used
 #pragma unroll
-        for (int j = 0; j < H; ++j) e[j] = en[j];
-        if (r + 1 < rows) {                       // next row's gains are in flight while this row computes
-          const uint32_t xn = (w4[(r + 1) >> 2] >> (8 * ((r + 1) & 3))) & 0xffu;
-#pragma unroll
-          for (int j = 0; j < H; ++j) en[j] = __ldg(rmb + (xn * H + j) * 32);
+          for (int j = 0; j < H; ++j) eg[rr][j] = __ldg(rmb + (x * H + j) * 32);
         }
-        uint32_t up = __shfl_up_sync(0xffffffffu, sv[H - 1], 1);
-        if (lane == 0) up = 0u;
-        const uint32_t in0 = __byte_perm(up, sv[H - 1], 0x5432);     // lo: position below my block, hi: my position Q/2
+        uint32_t cp[H];
 #pragma unroll
-        for (int j = H - 1; j >= 1; --j) sv[j] = __viaddmax_s16x2(__vmaxs2(sv[j - 1], XB), e[j], 0u);
-        sv[0] = __viaddmax_s16x2(__vmaxs2(in0, XB), e[0], 0u);
-        uint32_t xEv = sv[0];
-        if (H == 1) { }
-        else if (H & 1) {
+        for (int j = 0; j < H; ++j) cp[j] = sv[j];
+        uint32_t xEg = 0u;
 #pragma unroll
-          for (int j = 1; j + 1 < H; j += 2) xEv = __vimax3_s16x2(xEv, sv[j], sv[j + 1]);
-        } else {
-          xEv = __vmaxs2(xEv, sv[1]);
-#pragma unroll
-          for (int j = 2; j + 1 < H; j += 2) xEv = __vimax3_s16x2(xEv, sv[j], sv[j + 1]);
-        }
-        int xE = max((int)(xEv & 0xffffu), (int)(xEv >> 16));
+        for (int rr = 0; rr < 4; ++rr) if (rr < nrow) xEg = __vmaxs2(xEg, row(eg[rr], XB));
+        int xE = max((int)(xEg & 0xffffu), (int)(xEg >> 16));
         xE = __reduce_max_sync(0xffffffffu, xE);
-        if (xE + bias >= 255) { overflow = true; break; }
-        xE = max(xE - tec, 0);
-        xJ = max(xJ, xE);
-        xB = max(max(base, xJ) - tjbm, 0);
-        XB = (uint32_t)xB * 0x00010001u;
+        if (xE + bias < 255 && xE - tec <= max(base, xJ)) {
+          xJ = max(xJ, max(xE - tec, 0));
+        } else {
+#pragma unroll
+          for (int j = 0; j < H; ++j) sv[j] = cp[j];
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            if (rr < nrow && !overflow) {
+              const uint32_t xEv = row(eg[rr], XB);
+              int xe = max((int)(xEv & 0xffffu), (int)(xEv >> 16));
+              xe = __reduce_max_sync(0xffffffffu, xe);
+              if (xe + bias >= 255) overflow = true;
+              else {
+                xe = max(xe - tec, 0);
+                xJ = max(xJ, xe);
+                xB = max(max(base, xJ) - tjbm, 0);
+                XB = (uint32_t)xB * 0x00010001u;
+              }
+            }
+          }
+        }
       }
+      r16 = rnext;
     }
     if (lane == 0) {
       float usc;
