@@ -66,7 +66,7 @@ SYMBOLS = ["ckm_init", "ckm_destroy", "ckm_last_error", "ckm_version", "ckm_devi
            "ckm_models_load", "ckm_models_count", "ckm_models_info", "ckm_models_find", "ckm_models_select",
            "ckm_models_write", "ckm_models_free", "ckm_digitize", "ckm_seqdb_create", "ckm_seqdb_free",
            "ckm_search", "ckm_search_per_bin", "ckm_hits_free", "ckm_last_stats", "ckm_msv_scores",
-           "ckm_filter_scores", "ckm_write_domtblout", "ckm_reduce", "ckm_genome_check", "ckm_free", "ckm_allgather_qa"]
+           "ckm_filter_scores", "ckm_viterbi_scores", "ckm_write_domtblout", "ckm_reduce", "ckm_genome_check", "ckm_free", "ckm_allgather_qa"]
 
 _lib = None
 
@@ -105,6 +105,7 @@ def lib():
     L.ckm_last_stats.argtypes = [vp, C.POINTER(Stats)]
     L.ckm_msv_scores.argtypes = [vp, vp, vp, i32, vp, vp]
     L.ckm_filter_scores.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp]
+    L.ckm_viterbi_scores.argtypes = [vp, vp, vp, i32, vp, i32, vp]
     L.ckm_write_domtblout.argtypes = [vp, C.POINTER(Hit), i64, i32, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p),
                                       C.c_char_p]
     L.ckm_reduce.argtypes = [vp, i32, i32, i32, C.POINTER(Hit), i64, C.POINTER(ReduceOpts), C.POINTER(ReduceMeta),

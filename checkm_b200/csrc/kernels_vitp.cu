@@ -208,6 +208,22 @@ static int launch_vitp_w(const FilterParams &p, int grid, cudaStream_t st) {
   return e == cudaSuccess ? CKM_OK : cuda_fail(e, "vitp_kernel launch");
 }
 
+// every (model slot, sequence) pair as a candidate that still needs the Viterbi filter (parity entry point ckm_viterbi_scores)
+__global__ void all_pairs_kernel(Candidate *out, int32_t *count, const int32_t *slot_model, int32_t nslots, int32_t nseq) {
+  const int64_t n = (int64_t)nslots * nseq;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    Candidate cd;
+    cd.seq = (int32_t)(i % nseq); cd.model = slot_model[i / nseq]; cd.usc = 0.0f; cd.filtersc = 0.0f; cd.vitsc = 0.0f; cd.fwdsc = 0.0f; cd.P = 1.0;
+    out[i] = cd;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *count = (int32_t)n;
+}
+int launch_all_pairs(Candidate *out, int32_t *count, const int32_t *slot_model, int32_t nslots, int32_t nseq, cudaStream_t st) {
+  all_pairs_kernel<<<592, 256, 0, st>>>(out, count, slot_model, nslots, nseq);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? CKM_OK : cuda_fail(e, "all_pairs_kernel launch");
+}
+
 int launch_vitp(const FilterParams &p, int cls, int grid, cudaStream_t st) {
   switch (cls) {
     case 0: return launch_vitp_w<1, false>(p, grid, st);

@@ -658,6 +658,61 @@ int ckm_write_domtblout(const ckm_models *m, const ckm_hit *hits, int64_t nhits,
   return CKM_OK;
 }
 
+int ckm_viterbi_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_idx, int32_t nmodels,
+                       const ckm_seqdb *db, int32_t mode, float *vit_out) {
+  if (!e || !m || !db || !vit_out) { set_error("ckm_viterbi_scores: bad argument"); return CKM_EINVAL; }
+  cudaSetDevice(e->device);
+  cudaStream_t st = e->stream;
+  const int ndb = (int)m->models.size();
+  if (model_idx == nullptr) nmodels = ndb;
+  const int64_t n = (int64_t)nmodels * db->nseq;
+  if (n > ((int64_t)1 << 30)) { set_error("ckm_viterbi_scores: too many pairs for one call"); return CKM_ECAPACITY; }
+  PoolScope pool_scope(e);
+  ActiveMasks am; std::vector<int32_t> slot;
+  int rc = build_masks(m, db, model_idx, nmodels, nullptr, am, slot, st);
+  if (rc) return rc;
+  std::vector<int32_t> slot_model((size_t)std::max(nmodels, 1));
+  for (int i = 0; i < nmodels; ++i) slot_model[i] = model_idx ? model_idx[i] : i;
+  const size_t nf = (size_t)std::max<int64_t>(n, 1);
+  DevBuf dsm, din, dout, dredo, dvit;
+  if ((rc = dsm.alloc(sizeof(int32_t) * slot_model.size())) || (rc = din.alloc(sizeof(Candidate) * nf)) || (rc = dout.alloc(sizeof(Candidate) * nf)) ||
+      (rc = dredo.alloc(sizeof(Candidate) * nf)) || (rc = dvit.alloc(sizeof(float) * nf))) return rc;
+  CKM_CUDA(cudaMemcpyAsync(dsm.p, slot_model.data(), sizeof(int32_t) * slot_model.size(), cudaMemcpyHostToDevice, st));
+  CKM_CUDA(cudaMemsetAsync(e->d_counters, 0, CTR_N * sizeof(int32_t), st));
+  CKM_CUDA(cudaMemsetAsync(dvit.p, 0xff, sizeof(float) * nf, st));
+  std::memset(&e->stats, 0, sizeof(e->stats));
+  if (n > 0) {
+    if ((rc = launch_all_pairs(din.as<Candidate>(), e->d_counters + CTR_BIAS, dsm.as<int32_t>(), nmodels, db->nseq, st))) return rc;
+    const int nsm = e->prop.multiProcessorCount;
+    FilterParams p{};
+    p.res = db->d_res; p.off = db->d_off; p.len = db->d_len; p.lenA = db->d_lenA; p.lenB = db->d_lenB; p.tmove_w = db->d_tmove_w;
+    p.ms = m->d_scalars; p.bias_eo = m->d_bias_eo; p.rwv = m->d_rwv; p.twv = m->d_twv; p.rfv = m->d_rfv; p.tfv = m->d_tfv;
+    p.twb = m->d_twb; p.rwb = m->d_rwb; p.tfb = m->d_tfb; p.rfb = m->d_rfb; p.twp = m->d_twp; p.rwp = m->d_rwp;
+    p.row_elems = ((m->maxM + 31) / 32) * 32 + 64;
+    p.F1 = 0.02; p.F2 = 1e-3; p.F3 = 1e-5; p.use_blk = 1;
+    p.dense_vit = dvit.as<float>(); p.model_slot = am.model_slot.as<int32_t>(); p.nseq = db->nseq;
+    p.redo = dredo.as<Candidate>(); p.redo_count = e->d_counters + CTR_VREDO; p.redo_cap = (int32_t)nf;
+    p.in = din.as<Candidate>(); p.in_count = e->d_counters + CTR_BIAS; p.in_cap = (int32_t)nf;
+    p.out = dout.as<Candidate>(); p.out_count = e->d_counters + CTR_VIT; p.out_cap = (int32_t)nf;
+    if (mode == 0) {
+      if ((rc = fan_out(e))) return rc;
+      for (int c = 0; c < N_BLK_CLASSES; ++c) if ((rc = launch_vitp(p, c, nsm * 8, e->cls[c]))) return rc;
+      if ((rc = fan_in(e))) return rc;
+      p.in = dredo.as<Candidate>(); p.in_count = e->d_counters + CTR_VREDO;
+    }
+    if ((rc = fan_out(e))) return rc;
+    for (int c = 0; c < N_BLK_CLASSES; ++c) if ((rc = launch_vit2(p, c, nsm * 8, e->cls[c]))) return rc;
+    if ((rc = launch_vit(p, nsm * 4, e->cls[N_BLK_CLASSES]))) return rc;
+    if ((rc = fan_in(e))) return rc;
+  }
+  int32_t ctr[CTR_N];
+  CKM_CUDA(cudaMemcpyAsync(ctr, e->d_counters, sizeof(ctr), cudaMemcpyDeviceToHost, st));
+  CKM_CUDA(cudaMemcpyAsync(vit_out, dvit.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CKM_CUDA(cudaStreamSynchronize(st));
+  e->stats.n_pairs = n; e->stats.n_past_bias = ctr[CTR_BIAS]; e->stats.n_past_vit = ctr[CTR_VIT]; e->stats.n_vit_redo = ctr[CTR_VREDO];
+  return CKM_OK;
+}
+
 int ckm_msv_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_idx, int32_t nmodels,
                    const ckm_seqdb *db, int32_t *xj_out) {
   if (!e || !m || !db || !xj_out) { set_error("ckm_msv_scores: bad argument"); return CKM_EINVAL; }

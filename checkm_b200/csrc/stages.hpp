@@ -73,6 +73,7 @@ constexpr int N_BLK_CLASSES = 10;
 constexpr int BLK_Q[N_BLK_CLASSES] = {2, 4, 6, 8, 12, 16, 20, 24, 28, 32};
 int launch_vit2(const FilterParams &p, int cls, int grid, cudaStream_t st);
 int launch_vitp(const FilterParams &p, int cls, int grid, cudaStream_t st);   // packed int16x2 kernels (kernels_vitp.cu)
+int launch_all_pairs(Candidate *out, int32_t *count, const int32_t *slot_model, int32_t nslots, int32_t nseq, cudaStream_t st);
 int launch_fwd(const FilterParams &p, int grid, cudaStream_t st);
 
 // ---- stage 5: domain definition ----

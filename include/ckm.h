@@ -153,6 +153,12 @@ int  ckm_filter_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_
                        const ckm_seqdb *db, float *filtersc_out, float *vit_out, float *fwd_out,
                        uint8_t *passed_out /* bit0 msv, bit1 bias, bit2 vit, bit3 fwd; each nmodels*nseq */);
 
+/* ViterbiFilter score (nats) of EVERY pair, through the production kernels: the packed int16x2 kernel with its int32
+ * redo list (mode 0) or the int32 kernels alone (mode 1).  +inf = int16 overflow, -inf = no path.  n_vit_redo of
+ * ckm_last_stats says how many pairs took the redo route. */
+int  ckm_viterbi_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_idx, int32_t nmodels,
+                        const ckm_seqdb *db, int32_t mode, float *vit_out /* nmodels*nseq */);
+
 /* ---- domtblout text for one bin of a finished search: the file CheckM's HMMERParser re-reads
  * (checkm/hmmer.py:184-200).  names/descs are the FASTA header words of the bin's sequences. ---- */
 int  ckm_write_domtblout(const ckm_models *m, const ckm_hit *hits, int64_t nhits, int32_t bin,

@@ -138,6 +138,14 @@ def filters(hf, m, dsq):
     return r
 
 
+def vitfilter(hf, m, dsq):
+    """ViterbiFilter score (nats) of one pair; +inf on int16 overflow."""
+    d = np.ascontiguousarray(dsq, dtype=np.uint8)
+    sc = C.c_float()
+    lib().orc_vitfilter(hf.prof_ptrs[m], d.ctypes.data, len(d), C.byref(sc))
+    return sc.value
+
+
 def msv(hf, m, dsq):
     sc = C.c_float()
     xj = C.c_int()
