@@ -123,6 +123,15 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, 'fallback'
 
 
+def ssv_traffic():
+    """DRAM bytes per SSV launch from the committed `ncu --set full` capture (profiles/r1_ssv32_traffic.json), or None."""
+    p = os.path.join(ROOT, 'profiles', 'r1_ssv32_traffic.json')
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
 def oracle_sample(db_path, bins, nthreads, n_models=64):
     """CPU restatement on a bounded sample: bin 0 x the first `n_models` models; returns (seconds, sum M of the sample)."""
     from oracle import pyoracle as po
@@ -354,14 +363,24 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    def timed(nsteps, fn):
+        """nsteps steps between two device-wide synchronisations (+ barrier), timed on the device with CUDA events recorded
+        right after the first and right after the second synchronisation (the engines launch on their own streams, so the
+        events bracket the region rather than ride one stream); the host wall clock is kept as a cross-check."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync()
+        ev0.record()
+        t0 = time.perf_counter()
+        recs_ = run_steps(nsteps, fn)
+        sync()
+        ev1.record()
+        ev1.synchronize()
+        return recs_, ev0.elapsed_time(ev1) / 1e3, time.perf_counter() - t0
+
     run_steps(max(args.warmup, 0), step_resident)
     sampler = ClockSampler(local)
     sampler.start()
-    sync()
-    t0 = time.perf_counter()
-    recs = run_steps(args.steps, step_resident)
-    sync()
-    t_res = time.perf_counter() - t0
+    recs, t_res, t_res_wall = timed(args.steps, step_resident)
     ssv_ms = msv_ms = other_ms = 0.0
     launches = cells = pairs = 0
     for hits, st, rows, hm in recs:
@@ -374,11 +393,7 @@ def main():
         for k_, v_ in zip(('search', 'reduce', 'gather'), hm):
             host_ms[k_] += v_
     last = recs[-1][:3]
-    sync()
-    t0 = time.perf_counter()
-    recs_e = run_steps(args.steps, step_e2e)
-    sync()
-    t_e2e = time.perf_counter() - t0
+    recs_e, t_e2e, t_e2e_wall = timed(args.steps, step_e2e)
     # one batch at a time on one engine: the stage times of an undisturbed search (the SSV roofline is quoted on both)
     iso = []
     for i in range(2):
@@ -404,6 +419,7 @@ def main():
     resid = float(sum(len(b['res']) for b in batches[:1]))
     alg_bytes_per_step = resid * nm + 4.0 * (pairs / args.steps)
     peaks, peak_kind = measured_peaks()
+    traffic = ssv_traffic()
     ssv_s = (ssv_ms / args.steps) / 1000.0
     achieved = alg_bytes_per_step / ssv_s / 1e9
     real_cells = resid * sumM_all
@@ -419,20 +435,23 @@ def main():
             "e2e": {"value": e2e, "unit": "genomes/hour", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": achieved / peaks.get("hbm_gbs"),
-                         "traffic": None, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == 'measured' else 'fallback 6650',
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"), "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == 'measured' else 'fallback 6650',
                          "kernel": "ssv_kernel<J> (SSV pre-filter, all pairs)", "kernel_ms_per_step": ssv_ms / args.steps,
                          "isolated": {"kernel_ms": iso_ssv_ms, "achieved": alg_bytes_per_step / (iso_ssv_ms / 1e3) / 1e9,
                                       "frac": alg_bytes_per_step / (iso_ssv_ms / 1e3) / 1e9 / peaks.get("hbm_gbs"),
                                       "what": "same kernel, one batch in flight (no other stream on the SMs)"},
                          "note": "the stage is DP-cell bound, not HBM bound (SURVEY.md 8d): see gcups"},
             "gcups": {"real_cells_per_step": real_cells, "tile_cells_per_step": cells / args.steps, "ssv_gcups_real": real_cells / ssv_s / 1e9,
-                      "ssv_gcups_tile": cells / args.steps / ssv_s / 1e9, "ssv_gcups_real_isolated": real_cells / (iso_ssv_ms / 1e3) / 1e9, "smem_bound_gcups_at_1.9GHz": 148 * 51.2 * 1.9,
+                      "ssv_gcups_tile": cells / args.steps / ssv_s / 1e9, "ssv_gcups_real_isolated": real_cells / (iso_ssv_ms / 1e3) / 1e9, "smem_bound_gcups": 148 * (2048.0 / 35.0) * 1.965,
+                      "smem_bound_note": "J=32 tile row = 8 LDS.128 (32 wavefronts) + 1 SHFL (3) per 2048 cells at 1 wavefront/clk/SM, 148 SMs, 1.965 GHz",
+                      "ssv_frac_of_smem_bound": (cells / args.steps / ssv_s / 1e9) / (148 * (2048.0 / 35.0) * 1.965),
                       "stage_ms_per_step": {"ssv": ssv_ms / args.steps, "msv_exact": msv_ms / args.steps, "bias+vit+fwd+domdef": other_ms / args.steps,
                                             "wall_ms_per_step": {k_: v_ / args.steps for k_, v_ in host_ms.items()},
                                             "isolated_step": {"ssv": iso_st.ms_ssv, "msv_exact": iso_st.ms_msv, "bias": iso_st.ms_bias, "vit": iso_st.ms_vit, "fwd": iso_st.ms_fwd,
                                                               "domdef": iso_st.ms_domdef, "total": iso_st.ms_total}}},
             "cascade": {"pairs": int(st.n_pairs), "ssv_cand": int(st.n_ssv_cand), "past_msv": int(st.n_past_msv), "past_bias": int(st.n_past_bias),
-                        "past_vit": int(st.n_past_vit), "past_fwd": int(st.n_past_fwd), "rows": int(st.n_reported)},
+                        "past_vit": int(st.n_past_vit), "past_fwd": int(st.n_past_fwd), "rows": int(st.n_reported), "vit_int32_redo": int(st.n_vit_redo)},
+            "timing": {"how": "CUDA events around the K timed steps (after barrier + device synchronize on both sides), max over ranks", "host_wall_s": t_res_wall, "host_wall_e2e_s": t_e2e_wall},
             "clocks": sampler.summary()}
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1

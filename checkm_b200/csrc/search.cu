@@ -1,6 +1,8 @@
 // search.cu -- the search driver: launches the filter cascade and the domain-definition stages on the engine's
 // stream and assembles the hit table.  Replaces the body of `hmmsearch` behind checkm/hmmer.py:61-74.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -314,6 +316,19 @@ static std::vector<float> &logsum_table() {
 
 struct HostHit { int pair; HitOut h; int first_dom, ndom_slots; };
 
+// CKM_TRACE=1: host-side wall-clock marks of one search on stderr (where the time between the CUDA events goes)
+struct Trace {
+  bool on; std::chrono::steady_clock::time_point t0, last;
+  Trace() { const char *v = std::getenv("CKM_TRACE"); on = (v != nullptr && v[0] == '1'); t0 = last = std::chrono::steady_clock::now(); }
+  void mark(const char *what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[ckm trace] %-28s +%8.3f ms  (%9.3f)\n", what, std::chrono::duration<double, std::milli>(now - last).count(),
+                 std::chrono::duration<double, std::milli>(now - t0).count());
+    last = now;
+  }
+};
+
 static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_idx, int32_t nmodels, const int64_t *bin_model_offsets,
                      const ckm_seqdb *db, double Ecut, double domEcut, ckm_hit **hits_out, int64_t *nhits_out) {
   if (!e || !m || !db || !hits_out || !nhits_out) { set_error("ckm_search: bad argument"); return CKM_EINVAL; }
@@ -341,6 +356,7 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
   }
   std::memset(&e->stats, 0, sizeof(e->stats));
   CKM_CUDA(cudaEventRecord(e->ev[8], st));
+  Trace tr;
   Stage1 s1; Stage2 s2;
   if ((rc = run_stage1(e, m, db, am, std::max<int64_t>(n_pairs, 1), s1, nullptr))) return rc;
   if ((rc = run_stage2(e, m, db, am, s1, s2, nullptr, nullptr, nullptr, nullptr))) return rc;
@@ -349,6 +365,7 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
   CKM_CUDA(cudaMemcpyAsync(ctr, e->d_counters, sizeof(ctr), cudaMemcpyDeviceToHost, st));
   CKM_CUDA(cudaMemcpyAsync(&cells, s1.cells.p, sizeof(cells), cudaMemcpyDeviceToHost, st));
   CKM_CUDA(cudaStreamSynchronize(st));
+  tr.mark("filters done");
   if (ctr[CTR_CAND] > s1.cand_cap || ctr[CTR_MSV] > s1.pass_cap || ctr[CTR_BIAS] > s2.cap || ctr[CTR_VIT] > s2.cap || ctr[CTR_FWD] > s2.cap) {
     set_error("candidate queue overflow in the filter cascade"); return CKM_ECAPACITY;
   }
@@ -373,6 +390,7 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
   std::vector<DomainOut> doms; std::vector<HitOut> hout((size_t)npairs);
   std::vector<Envelope> envs;
   CKM_CUDA(cudaEventRecord(e->ev[6], st));
+  tr.mark("pair list sorted");
   if (npairs > 0) {
     const size_t rws = (size_t)std::max<int64_t>(rows, 1);
     if ((rc = dpairs.alloc(sizeof(PairWork) * pairs.size())) || (rc = dxf.alloc(sizeof(float) * rws * X_NX_HOST)) || (rc = dxb.alloc(sizeof(float) * rws * X_NX_HOST)) ||
@@ -415,6 +433,7 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
       }
       if ((rc = fan_in(e))) return rc;
       CKM_CUDA(cudaStreamSynchronize(st));   // `order` is read by the copy above
+      tr.mark("regions kernels");
     }
     int32_t nreg = 0;
     CKM_CUDA(cudaMemcpyAsync(&nreg, e->d_counters + CTR_ENV, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -423,6 +442,7 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
     std::vector<Region> regs((size_t)nreg);
     if (nreg) CKM_CUDA(cudaMemcpy(regs.data(), dregions.p, sizeof(Region) * regs.size(), cudaMemcpyDeviceToHost));
     std::sort(regs.begin(), regs.end(), [](const Region &a, const Region &b) { return a.pair != b.pair ? a.pair < b.pair : a.i < b.i; });
+    tr.mark("regions sorted");
     // Domain slots.  Regions are sorted by (pair, start), so a pair's slots are contiguous and in sequence order: one slot
     // per single-domain region, ENS_MAXENV per multi-domain region (the ensemble decides how many it fills; unused slots
     // keep ok = 0 and are skipped by every consumer).  Fixing the slots before the ensemble has run lets the envelopes of
@@ -510,6 +530,7 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
       // the other way round the two compete for the memory system and the ensemble's dependent loads take 2-3x longer.)
       EnsembleJob *job = nullptr;
       if ((rc = run_env_batch(envs1, denvs, deorder, !multi_idx.empty()))) return rc;
+      tr.mark("envelope batch 1 launched");
       if (!multi_idx.empty()) {
         CKM_CUDA(cudaEventRecord(e->fan_ev, st));
         CKM_CUDA(cudaStreamWaitEvent(e->aux, e->fan_ev, 0));
@@ -519,11 +540,13 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
       if (job != nullptr) {
         std::vector<std::vector<Envelope>> multi_envs;
         if ((rc = ensembles_collect(job, e->aux, multi_envs))) return rc;
+        tr.mark("batch 1 + ensemble done");
         for (size_t mi = 0; mi < multi_idx.size(); ++mi) {
           int c = 0;
           for (Envelope en : multi_envs[mi]) { if (c >= ENS_MAXENV) break; en.slot = reg_slot[multi_idx[mi]] + c++; envs2.push_back(en); }
         }
         if ((rc = run_env_batch(envs2, denvs2, deorder2, false))) return rc;
+        tr.mark("envelope batch 2 done");
       }
       p.hits = dhits.as<HitOut>();
       if ((rc = launch_scores(p, (npairs + 127) / 128, st))) return rc;
@@ -537,6 +560,7 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
   }
   CKM_CUDA(cudaEventRecord(e->ev[7], st));
   CKM_CUDA(cudaEventSynchronize(e->ev[7]));
+  tr.mark("scores + downloads");
 
   // ---- thresholds, ordering, rows (bookkeeping on the hit list; hmmsearch's output phase) ----
   struct Key { int bin, q, pair; double lnP; int seq; };
@@ -589,6 +613,7 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
     }
     g0 = g1;
   }
+  tr.mark("rows assembled");
   e->stats.n_hits_seq = (int64_t)keys.size(); e->stats.n_domains = n_dom; e->stats.n_reported = (int64_t)rows_out.size();
   cudaEventElapsedTime(&e->stats.ms_ssv, e->ev[0], e->ev[1]);
   cudaEventElapsedTime(&e->stats.ms_msv, e->ev[1], e->ev[2]);
