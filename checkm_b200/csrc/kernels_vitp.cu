@@ -1,6 +1,6 @@
 // kernels_vitp.cu -- ViterbiFilter on packed int16x2 lanes (two model positions per 32-bit register, one DPX
 // VIADDMNMX.S16x2 per add+max of both).  Stage 3 of the cascade behind checkm/hmmer.py:70-71; same result as the
-// int32 kernels of kernels_filters.cu (and as oracle/hmmer_oracle.c:orc_vitfilter), at ~4.5 ALU instructions per DP
+// int32 kernels of kernels_filters.cu (the int16-saturating recurrence of SURVEY.md A.5 step 3), at ~4.5 ALU instructions per DP
 // cell instead of ~11.
 //
 // Layout.  W = vq/2 words per lane, K = 64 W cells.  Word w of lane l holds position k0 = l*W + w + 1 in its low
