@@ -53,10 +53,10 @@ __device__ __forceinline__ void ssv_rows(const uint8_t *__restrict__ res, int L,
 #pragma unroll
       for (int q = J - 1; q >= 1; --q) {
         const uint32_t d = (&e[q >> 2].x)[q & 3];
-        u[q] = __viaddmax_s16x2(u[q - 1], d, 0u);
+        u[q] = __viaddmax_s16x2_relu(u[q - 1], d, 0x80008000u);     // max(u + d, 0): the relu form takes its floor as an immediate (a literal 0 operand costs a register zeroing per use)
       }
       const uint32_t p0 = __byte_perm(sh, bndw, sel);
-      u[0] = __viaddmax_s16x2(p0, e[0].x, 0u);
+      u[0] = __viaddmax_s16x2_relu(p0, e[0].x, 0x80008000u);
 #pragma unroll
       for (int q = 0; q < J; q += 2) xE = __vimax3_s16x2(xE, u[q], u[q + 1]);
       if (bnd_out != nullptr && lane == 31) bnd_out[b * 16 + r] = (int16_t)(u[J - 1] >> 16);
@@ -318,8 +318,8 @@ __global__ void __launch_bounds__(128) msv2_kernel(MsvParams p) {
       if (lane == 0) up = 0u;
       const uint32_t in0 = __byte_perm(up, sv[H - 1], 0x5432);     // lo: position below my block, hi: my position Q/2
 #pragma unroll
-      for (int j = H - 1; j >= 1; --j) sv[j] = __viaddmax_s16x2(__vmaxs2(sv[j - 1], XBw), e[j], 0u);
-      sv[0] = __viaddmax_s16x2(__vmaxs2(in0, XBw), e[0], 0u);
+      for (int j = H - 1; j >= 1; --j) sv[j] = __viaddmax_s16x2_relu(__vmaxs2(sv[j - 1], XBw), e[j], 0x80008000u);
+      sv[0] = __viaddmax_s16x2_relu(__vmaxs2(in0, XBw), e[0], 0x80008000u);
       uint32_t xEv = sv[0];
       if (H == 1) { }
       else if (H & 1) {
