@@ -435,7 +435,7 @@ def main():
             "e2e": {"value": e2e, "unit": "genomes/hour", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": achieved / peaks.get("hbm_gbs"),
-                         "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"), "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == 'measured' else 'fallback 6650',
+                         "traffic": (traffic["dram_bytes_per_bin"] * B) if traffic else None, "traffic_source": (traffic or {}).get("source"), "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == 'measured' else 'fallback 6650',
                          "kernel": "ssv_kernel<J> (SSV pre-filter, all pairs)", "kernel_ms_per_step": ssv_ms / args.steps,
                          "isolated": {"kernel_ms": iso_ssv_ms, "achieved": alg_bytes_per_step / (iso_ssv_ms / 1e3) / 1e9,
                                       "frac": alg_bytes_per_step / (iso_ssv_ms / 1e3) / 1e9 / peaks.get("hbm_gbs"),
@@ -444,7 +444,8 @@ def main():
             "gcups": {"real_cells_per_step": real_cells, "tile_cells_per_step": cells / args.steps, "ssv_gcups_real": real_cells / ssv_s / 1e9,
                       "ssv_gcups_tile": cells / args.steps / ssv_s / 1e9, "ssv_gcups_real_isolated": real_cells / (iso_ssv_ms / 1e3) / 1e9, "smem_bound_gcups": 148 * (2048.0 / 35.0) * 1.965,
                       "smem_bound_note": "J=32 tile row = 8 LDS.128 (32 wavefronts) + 1 SHFL (3) per 2048 cells at 1 wavefront/clk/SM, 148 SMs, 1.965 GHz",
-                      "ssv_frac_of_smem_bound": (cells / args.steps / ssv_s / 1e9) / (148 * (2048.0 / 35.0) * 1.965),
+                      "ssv_gcups_tile_isolated": cells / args.steps / (iso_ssv_ms / 1e3) / 1e9,
+                      "ssv_frac_of_smem_bound": (cells / args.steps / (iso_ssv_ms / 1e3) / 1e9) / (148 * (2048.0 / 35.0) * 1.965),
                       "stage_ms_per_step": {"ssv": ssv_ms / args.steps, "msv_exact": msv_ms / args.steps, "bias+vit+fwd+domdef": other_ms / args.steps,
                                             "wall_ms_per_step": {k_: v_ / args.steps for k_, v_ in host_ms.items()},
                                             "isolated_step": {"ssv": iso_st.ms_ssv, "msv_exact": iso_st.ms_msv, "bias": iso_st.ms_bias, "vit": iso_st.ms_vit, "fwd": iso_st.ms_fwd,
