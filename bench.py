@@ -165,6 +165,11 @@ def total_model_positions(db_path):
     return tot
 
 
+def workload_name(sumM_all):
+    return ("configs[2] stand-in: synthetic 3 Mb bins (2,900 ORFs, ~0.9 M residues, 0-2 planted homologs per CPR family) x 5,000 HMMs "
+            "(the 43 real HMMER-calibrated CPR models x 116 replicas under distinct accessions, sum M = %d)" % sumM_all)
+
+
 def run_reference(args):
     rank, local, world = rank_info()
     if rank != 0:
@@ -186,8 +191,9 @@ def run_reference(args):
     line = {"metric": "genomes/hour", "value": gph, "unit": "genomes/hour", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int16/f32",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": "configs[2] stand-in: synthetic 3 Mb bins x 5,000 HMMs (43 real CPR models x 116 replicas)", "bins_per_step": 1,
-                       "orfs_per_bin": ORFS_PER_BIN, "n_models": N_MODELS},
+            "config": {"workload": workload_name(sumM_all), "bins_per_step": args.bins_per_step, "orfs_per_bin": ORFS_PER_BIN, "n_models": N_MODELS,
+                       "per_gpu_bins_per_step": args.bins_per_step, "parallelism": "CPU: one thread per ORF block, all host cores",
+                       "sample_per_step": sample},
             "cpu_baseline": {"value": gph, "unit": "genomes/hour", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": gph, "unit": "genomes/hour", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -428,7 +434,7 @@ def main():
     line = {"metric": "genomes/hour", "value": value, "unit": "genomes/hour", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16 (SSV) / u8 (MSV) / int16 (Viterbi) / f32 (Forward, domain definition)", "data": "synthetic",
-            "config": {"workload": "configs[2] stand-in: synthetic 3 Mb bins (2,900 ORFs, ~0.9 M residues, 0-2 planted homologs per CPR family) x 5,000 HMMs (the 43 real HMMER-calibrated CPR models x 116 replicas under distinct accessions, sum M = %d)" % sumM_all,
+            "config": {"workload": workload_name(sumM_all),
                        "bins_per_step": B, "orfs_per_bin": ORFS_PER_BIN, "n_models": nm, "per_gpu_bins_per_step": B, "parallelism": "bins sharded, 1 process/GPU",
                        "batches_in_flight_per_gpu": NP,
                        "l2": "256 MiB flush write issued before every step; the model tables alone (> 200 MB) exceed L2", "model_load_s": t_load},
