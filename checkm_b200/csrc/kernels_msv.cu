@@ -31,37 +31,41 @@ __device__ __forceinline__ void ssv_rows(const uint8_t *__restrict__ res, int L,
                                          const int16_t *bnd_in, int16_t *bnd_out, uint32_t (&u)[J], uint32_t &xE) {
   constexpr int G = J / 4;
   const uint4 *rp = reinterpret_cast<const uint4 *>(res);
-  const int nblk = (L + 15) >> 4;
-  uint4 cur = __ldg(rp);
   const uint32_t lane_off = tile_smem + lane * 16;
-  for (int b = 0; b < nblk; ++b) {
-    uint4 nxt = (b + 1 < nblk) ? __ldg(rp + b + 1) : cur;
+  auto do_row = [&](uint32_t x, int i) {
+    const uint32_t row = lane_off + x * (128 * J);
+    uint4 e[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) e[g] = lds128(row + g * 512);
+    uint32_t bndw = 0;
+    if (bnd_in != nullptr) bndw = (i > 0) ? (uint32_t)(uint16_t)bnd_in[i - 1] : 0u;      // chained tile: cell 0 continues the previous chunk's last cell
+    const uint32_t sh = __shfl_sync(0xffffffffu, u[J - 1], (lane + 31) & 31);
+#pragma unroll
+    for (int q = J - 1; q >= 1; --q) {
+      const uint32_t d = (&e[q >> 2].x)[q & 3];
+      u[q] = __viaddmax_s16x2_relu(u[q - 1], d, 0x80008000u);     // max(u + d, 0): the relu form takes its floor as an immediate (a literal 0 operand costs a register zeroing per use)
+    }
+    const uint32_t p0 = __byte_perm(sh, bndw, sel);
+    u[0] = __viaddmax_s16x2_relu(p0, e[0].x, 0x80008000u);
+#pragma unroll
+    for (int q = 0; q < J; q += 2) xE = __vimax3_s16x2(xE, u[q], u[q + 1]);
+    if (bnd_out != nullptr && lane == 31) bnd_out[i] = (int16_t)(u[J - 1] >> 16);
+  };
+  // full blocks of 16 rows, then the tail in groups of 4 (at most 3 padding rows are swept; they score -inf everywhere)
+  const int nfull = L >> 4;
+  uint4 cur = __ldg(rp);
+  for (int b = 0; b < nfull; ++b) {
+    const uint4 nxt = __ldg(rp + b + 1);          // the stream is padded to a multiple of 16 and the next ORF (or the buffer's slack) follows
     const uint32_t w4[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      const uint32_t x = (w4[r >> 2] >> (8 * (r & 3))) & 0xffu;
-      const uint32_t row = lane_off + x * (128 * J);
-      uint4 e[G];
-#pragma unroll
-      for (int g = 0; g < G; ++g) e[g] = lds128(row + g * 512);
-      uint32_t bndw = 0;
-      if (bnd_in != nullptr) {              // chained tile: cell 0 continues the previous chunk's last cell
-        const int i = b * 16 + r;
-        bndw = (i > 0) ? (uint32_t)(uint16_t)bnd_in[i - 1] : 0u;
-      }
-      const uint32_t sh = __shfl_sync(0xffffffffu, u[J - 1], (lane + 31) & 31);
-#pragma unroll
-      for (int q = J - 1; q >= 1; --q) {
-        const uint32_t d = (&e[q >> 2].x)[q & 3];
-        u[q] = __viaddmax_s16x2_relu(u[q - 1], d, 0x80008000u);     // max(u + d, 0): the relu form takes its floor as an immediate (a literal 0 operand costs a register zeroing per use)
-      }
-      const uint32_t p0 = __byte_perm(sh, bndw, sel);
-      u[0] = __viaddmax_s16x2_relu(p0, e[0].x, 0x80008000u);
-#pragma unroll
-      for (int q = 0; q < J; q += 2) xE = __vimax3_s16x2(xE, u[q], u[q + 1]);
-      if (bnd_out != nullptr && lane == 31) bnd_out[b * 16 + r] = (int16_t)(u[J - 1] >> 16);
-    }
+    for (int r = 0; r < 16; ++r) do_row((w4[r >> 2] >> (8 * (r & 3))) & 0xffu, b * 16 + r);
     cur = nxt;
+  }
+  const int ntail = ((L & 15) + 3) >> 2;
+  for (int t = 0; t < ntail; ++t) {
+    const uint32_t w = (t == 0) ? cur.x : (t == 1) ? cur.y : (t == 2) ? cur.z : cur.w;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) do_row((w >> (8 * r)) & 0xffu, nfull * 16 + t * 4 + r);
   }
 }
 

@@ -211,8 +211,9 @@ static int run_stage2(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
   p.in = s2.b.as<Candidate>(); p.in_count = e->d_counters + CTR_VIT; p.in_cap = s2.cap;
   p.out = s2.a.as<Candidate>(); p.out_count = e->d_counters + CTR_FWD; p.out_cap = s2.cap;
   if ((rc = fan_out(e))) return rc;
-  if (p.use_blk) { for (int c = 0; c < N_BLK_CLASSES; ++c) if ((rc = launch_fwd2(p, c, nsm * 8, e->cls[c]))) return rc; }
+  // widest classes first: their one-warp-per-pair kernels are the long pole of the stage, the narrow ones fill in around them
   if ((rc = launch_fwd(p, nsm * 4, e->cls[N_BLK_CLASSES]))) return rc;
+  if (p.use_blk) { for (int c = N_BLK_CLASSES - 1; c >= 0; --c) if ((rc = launch_fwd2(p, c, nsm * 8, e->cls[c]))) return rc; }
   if ((rc = fan_in(e))) return rc;
   CKM_CUDA(cudaEventRecord(e->ev[5], st));
   e->stats.kernel_launches += 3 + N_BLK_CLASSES + (p.use_blk ? N_BLK_CLASSES : 0);
@@ -410,11 +411,11 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
     p.row_elems = ((m->maxM + 31) / 32) * 32 + 64;
     p.tfb = m->d_tfb; p.rfb = m->d_rfb; p.use_blk = use_blocked_kernels() ? 1 : 0;
     {
-      // pairs grouped by class, longest target first inside a class; every class runs on its own stream
+      // pairs grouped by class (widest class first: it is the long pole), longest target first inside a class; every class runs on its own stream
       std::vector<int32_t> order((size_t)npairs);
       std::vector<int8_t> pcls((size_t)npairs);
       for (int i = 0; i < npairs; ++i) { order[i] = i; pcls[i] = (int8_t)cls_of(m->models[pairs[i].model].M, p.use_blk != 0); }
-      std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return pcls[a] != pcls[b] ? pcls[a] < pcls[b] : pairs[a].L > pairs[b].L; });
+      std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return pcls[a] != pcls[b] ? pcls[a] > pcls[b] : pairs[a].L > pairs[b].L; });
       if ((rc = dporder.alloc(sizeof(int32_t) * order.size()))) return rc;
       CKM_CUDA(cudaMemcpyAsync(dporder.p, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice, st));
       p.pair_order = dporder.as<int32_t>();
@@ -499,7 +500,7 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
           if (tot > cur_alloc) { if ((rc2 = dscratch.alloc(sizeof(float) * (size_t)tot))) return rc2; cur_alloc = tot; }
           // this wave's envelopes grouped by class, largest first; one stream per class
           for (size_t i = w0; i < w1; ++i) eorder[i] = (int32_t)i;
-          std::stable_sort(eorder.begin() + w0, eorder.begin() + w1, [&](int32_t a, int32_t b) { return ecls[a] != ecls[b] ? ecls[a] < ecls[b] : need[a] > need[b]; });
+          std::stable_sort(eorder.begin() + w0, eorder.begin() + w1, [&](int32_t a, int32_t b) { return ecls[a] != ecls[b] ? ecls[a] > ecls[b] : need[a] > need[b]; });
           CKM_CUDA(cudaMemcpyAsync(d_ev.as<Envelope>() + w0, ev.data() + w0, sizeof(Envelope) * (w1 - w0), cudaMemcpyHostToDevice, st));
           CKM_CUDA(cudaMemcpyAsync(d_ord.as<int32_t>() + w0, eorder.data() + w0, sizeof(int32_t) * (w1 - w0), cudaMemcpyHostToDevice, st));
           p.envs = d_ev.as<Envelope>(); p.env_order = d_ord.as<int32_t>(); p.scratch = dscratch.as<float>();
