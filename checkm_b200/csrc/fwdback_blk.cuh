@@ -11,6 +11,8 @@
 
 namespace ckm {
 
+constexpr int BLK_LOOKAHEAD_MAXQ = 16;
+
 template <int Q, bool TSMEM>
 struct BlkModel {
   int M;
@@ -56,20 +58,28 @@ __device__ __forceinline__ float forward_blk(const BlkModel<Q, TSMEM> &bm, const
   }
   float xE = 0.0f, xN = 1.0f, xJ = 0.0f, xB = sp.nmove, xC = 0.0f, totscale = 0.0f;
   if (xmx != nullptr && lane == 0) { xmx[X_E] = xE; xmx[X_N] = xN; xmx[X_J] = xJ; xmx[X_B] = xB; xmx[X_C] = xC; xmx[X_SCALE] = 1.0f; }
+  constexpr bool LA = (Q <= BLK_LOOKAHEAD_MAXQ);      // the look-ahead row costs Q registers; the widest classes cannot afford it
   float ecur[Q];
-  {
+  int xnext;
+  if (LA) {
     const float *rp = bm.rfb + (size_t)((L >= 1) ? __ldg(res) : 0) * Q * 32;
 #pragma unroll
     for (int q = 0; q < Q; ++q) ecur[q] = __ldg(rp + q * 32);
-  }
-  int xnext = (L >= 2) ? __ldg(res + 1) : 0;
+    xnext = (L >= 2) ? __ldg(res + 1) : 0;
+  } else xnext = (L >= 1) ? __ldg(res) : 0;
   for (int i = 1; i <= L; ++i) {
-    float enext[Q];
+    float enext[LA ? Q : 1];
     {
       const float *rp = bm.rfb + (size_t)xnext * Q * 32;
+      if (LA) {
 #pragma unroll
-      for (int q = 0; q < Q; ++q) enext[q] = __ldg(rp + q * 32);
-      xnext = (i + 2 <= L) ? __ldg(res + i + 1) : 0;
+        for (int q = 0; q < Q; ++q) enext[LA ? q : 0] = __ldg(rp + q * 32);
+        xnext = (i + 2 <= L) ? __ldg(res + i + 1) : 0;
+      } else {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) ecur[q] = __ldg(rp + q * 32);
+        xnext = (i + 1 <= L) ? __ldg(res + i) : 0;
+      }
     }
     float pm_in = __shfl_up_sync(0xffffffffu, Mx[Q - 1], 1), pi_in = __shfl_up_sync(0xffffffffu, Ix[Q - 1], 1), pd_in = __shfl_up_sync(0xffffffffu, Dx[Q - 1], 1);
     if (lane == 0) { pm_in = 0.0f; pi_in = 0.0f; pd_in = 0.0f; }
@@ -131,8 +141,10 @@ __device__ __forceinline__ float forward_blk(const BlkModel<Q, TSMEM> &bm, const
       float *xr = xmx + (size_t)i * X_NX;
       xr[X_E] = xE; xr[X_N] = xN; xr[X_J] = xJ; xr[X_B] = xB; xr[X_C] = xC; xr[X_SCALE] = scale;
     }
+    if (LA) {
 #pragma unroll
-    for (int q = 0; q < Q; ++q) ecur[q] = enext[q];
+      for (int q = 0; q < Q; ++q) ecur[q] = enext[LA ? q : 0];
+    }
   }
   return totscale + (float)log((double)(xC * sp.nmove));
 }
@@ -150,17 +162,23 @@ __device__ __forceinline__ void backward_blk(const BlkModel<Q, TSMEM> &bm, const
 #pragma unroll
   for (int q = 0; q < Q; ++q) { Mx[q] = 0.0f; Ix[q] = 0.0f; Dx[q] = 0.0f; }
   float xC = 0.0f, xE = 0.0f, xJ = 0.0f, xN = 0.0f, xB = 0.0f;
-  float ecur[Q];          // emission row of residue x_{i+1}; fetched one iteration ahead
+  constexpr bool LA = (Q <= BLK_LOOKAHEAD_MAXQ);
+  float ecur[Q];          // emission row of residue x_{i+1}; fetched one iteration ahead when registers allow
 #pragma unroll
   for (int q = 0; q < Q; ++q) ecur[q] = 0.0f;
   int xnext = (L >= 1) ? __ldg(res + L - 1) : 0;
   for (int i = L; i >= 0; --i) {
-    float enext[Q];
-    {
+    float enext[LA ? Q : 1];
+    if (LA) {
       const float *rp = bm.rfb + (size_t)xnext * Q * 32;
 #pragma unroll
-      for (int q = 0; q < Q; ++q) enext[q] = __ldg(rp + q * 32);
+      for (int q = 0; q < Q; ++q) enext[LA ? q : 0] = __ldg(rp + q * 32);
       xnext = (i >= 2) ? __ldg(res + i - 2) : 0;
+    } else if (i < L) {
+      const float *rp = bm.rfb + (size_t)xnext * Q * 32;      // xnext == res[i] here
+#pragma unroll
+      for (int q = 0; q < Q; ++q) ecur[q] = __ldg(rp + q * 32);
+      xnext = (i >= 1) ? __ldg(res + i - 1) : 0;
     }
     if (MODE == 2 && i >= 3) {     // pull row i-2 of the Forward matrix towards L2 (M plane, I plane: Q lines each)
       const float *fr = full + (size_t)(i - 2) * 3 * Q * 32;
@@ -256,8 +274,10 @@ __device__ __forceinline__ void backward_blk(const BlkModel<Q, TSMEM> &bm, const
       float *xr = bxmx + (size_t)i * X_NX;
       xr[X_E] = xE; xr[X_N] = xN; xr[X_J] = xJ; xr[X_B] = xB; xr[X_C] = xC; xr[X_SCALE] = s;
     }
+    if (LA) {
 #pragma unroll
-    for (int q = 0; q < Q; ++q) ecur[q] = enext[q];
+      for (int q = 0; q < Q; ++q) ecur[q] = enext[LA ? q : 0];
+    }
   }
 }
 
