@@ -32,7 +32,7 @@ CPR = os.path.join(ROOT, 'tests', 'golden', 'cpr_43_markers.hmm')
 
 N_MODELS = 5000
 ORFS_PER_BIN = 2900
-BINS_PER_STEP = 8
+BINS_PER_STEP = 16
 
 
 def rank_info():

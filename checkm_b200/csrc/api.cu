@@ -6,6 +6,7 @@
 #include <fstream>
 #include <numeric>
 #include <stdexcept>
+#include <atomic>
 #include "engine.hpp"
 
 namespace ckm {
@@ -15,6 +16,8 @@ void models_free_device(ckm_models &db);
 }  // namespace ckm
 
 using namespace ckm;
+
+namespace ckm { extern std::atomic<int> g_live_engines; }
 
 extern "C" {
 
@@ -56,12 +59,14 @@ int ckm_init(int device, ckm_engine **out) {
     if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) { uint64_t keep = ~0ull; cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep); }
   }
   std::memset(&eng->stats, 0, sizeof(eng->stats));
+  ckm::g_live_engines.fetch_add(1);
   *out = eng;
   return CKM_OK;
 }
 
 void ckm_destroy(ckm_engine *e) {
   if (!e) return;
+  ckm::g_live_engines.fetch_sub(1);
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   for (auto &ev : e->ev) cudaEventDestroy(ev);

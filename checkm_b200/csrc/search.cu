@@ -1,6 +1,7 @@
 // search.cu -- the search driver: launches the filter cascade and the domain-definition stages on the engine's
 // stream and assembles the hit table.  Replaces the body of `hmmsearch` behind checkm/hmmer.py:61-74.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cmath>
@@ -15,6 +16,7 @@ using namespace ckm;
 
 namespace ckm {
 
+std::atomic<int> g_live_engines{0};     // engines alive in this process: they share the envelope-scratch budget
 thread_local ckm_engine *g_pool_engine = nullptr;
 thread_local int g_pool_next = 0;
 
@@ -472,8 +474,10 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
       size_t free_b = 0, total_b = 0;
       cudaMemGetInfo(&free_b, &total_b);
       (void)free_b;
-      // fixed scratch budget (the cached pool is reused by every later search): 1/3 of the device, at most 56 GiB
-      const int64_t budget0 = (int64_t)std::min<size_t>(total_b / 3, (size_t)56 << 30) / (int64_t)sizeof(float);
+      // fixed scratch budget (the cached pool is reused by every later search): 60% of the device shared by the live engines,
+      // at most 56 GiB each
+      const size_t neng = (size_t)std::max(1, g_live_engines.load());
+      const int64_t budget0 = (int64_t)std::min<size_t>(total_b * 6 / 10 / neng, (size_t)56 << 30) / (int64_t)sizeof(float);
       int64_t cur_alloc = 0;
       // Rescores a batch of envelopes: 2 matrices + specials of scratch each, in waves under the budget, every class on its
       // own stream.  leave_last: the last wave is left running on the class streams (the caller joins them with fan_in).
