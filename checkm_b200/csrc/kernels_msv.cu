@@ -308,22 +308,26 @@ __global__ void __launch_bounds__(128) msv2_kernel(MsvParams p) {
     const int tjb = p.tjb[s];
     const int tjbm = min(tjb + (int)ms.tbm_b, 255);
     const int bias = ms.bias_b, base = ms.base_b, tec = ms.tec_b;
+    // The registers hold u = max(sv, xB) - xB >= 0 (as the SSV pre-filter does), so a row is u' = max(u + gain, 0): one
+    // VIADDMNMX.RELU per word instead of a max with xB and an add.  max_k u' + xB = max(xE, xB), and using that in place of
+    // xE changes neither the xB trajectory (it can only lift an xJ that is still below base, which xB ignores) nor the final
+    // xJ as long as some cell of the pair was positive (then the best row has xE > xB).  When xB moves by delta, u is
+    // re-based: u <- max(u - delta, 0).  A pair without a single positive cell falls back to the plain recurrence.
     uint32_t sv[H];
 #pragma unroll
     for (int j = 0; j < H; ++j) sv[j] = 0u;
     int xJ = 0, xB = max(base - tjbm, 0);
-    uint32_t XB = (uint32_t)xB * 0x00010001u;
     bool overflow = false;
+    int umax = 0;
     const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + p.off[s]);
     const int nblk = (L + 15) >> 4;
-    // One row: sv <- max(max(shifted sv, xB) + gain, 0); returns the packed row maximum.
-    auto row = [&](const uint32_t (&e)[H], uint32_t XBw) -> uint32_t {
+    auto row = [&](const uint32_t (&e)[H]) -> uint32_t {
       uint32_t up = __shfl_up_sync(0xffffffffu, sv[H - 1], 1);
       if (lane == 0) up = 0u;
       const uint32_t in0 = __byte_perm(up, sv[H - 1], 0x5432);     // lo: position below my block, hi: my position Q/2
 #pragma unroll
-      for (int j = H - 1; j >= 1; --j) sv[j] = __viaddmax_s16x2_relu(__vmaxs2(sv[j - 1], XBw), e[j], 0x80008000u);
-      sv[0] = __viaddmax_s16x2_relu(__vmaxs2(in0, XBw), e[0], 0x80008000u);
+      for (int j = H - 1; j >= 1; --j) sv[j] = __viaddmax_s16x2_relu(sv[j - 1], e[j], 0x80008000u);
+      sv[0] = __viaddmax_s16x2_relu(in0, e[0], 0x80008000u);
       uint32_t xEv = sv[0];
       if (H == 1) { }
       else if (H & 1) {
@@ -336,10 +340,10 @@ __global__ void __launch_bounds__(128) msv2_kernel(MsvParams p) {
       }
       return xEv;
     };
-    // Rows go in groups of four with xB held fixed and ONE warp reduction per group: xB = max(base, xJ) - tjbm moves only
-    // when some row's xE - tec exceeds max(base, xJ), and while it does not, xJ after the group is max(xJ, group max - tec)
-    // -- exactly what the row-by-row recurrence gives.  A group whose maximum could move xB (or overflow) is replayed row by
-    // row from the saved registers; that happens only around the few high-scoring rows of a pair.
+    // Rows go in groups of four with ONE warp reduction per group: xB = max(base, xJ) - tjbm moves only when some row's
+    // xE - tec exceeds max(base, xJ), and while it does not, xJ after the group is max(xJ, group max - tec) -- exactly what the
+    // row-by-row recurrence gives.  A group whose maximum could move xB (or overflow) is replayed row by row from the saved
+    // registers; that happens only around the few high-scoring rows of a pair.
     uint4 r16 = (nblk > 0) ? __ldg(rp) : make_uint4(0, 0, 0, 0);
     for (int b = 0; b < nblk && !overflow; ++b) {
       const uint4 rnext = (b + 1 < nblk) ? __ldg(rp + b + 1) : make_uint4(0, 0, 0, 0);
@@ -360,32 +364,67 @@ __global__ void __launch_bounds__(128) msv2_kernel(MsvParams p) {
         for (int j = 0; j < H; ++j) cp[j] = sv[j];
         uint32_t xEg = 0u;
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) if (rr < nrow) xEg = __vmaxs2(xEg, row(eg[rr], XB));
-        int xE = max((int)(xEg & 0xffffu), (int)(xEg >> 16));
-        xE = __reduce_max_sync(0xffffffffu, xE);
+        for (int rr = 0; rr < 4; ++rr) if (rr < nrow) xEg = __vmaxs2(xEg, row(eg[rr]));
+        int uE = max((int)(xEg & 0xffffu), (int)(xEg >> 16));
+        uE = __reduce_max_sync(0xffffffffu, uE);
+        const int xE = uE + xB;                               // = max(row maxima of sv, xB)
         if (xE + bias < 255 && xE - tec <= max(base, xJ)) {
           xJ = max(xJ, max(xE - tec, 0));
+          umax = max(umax, uE);
         } else {
 #pragma unroll
           for (int j = 0; j < H; ++j) sv[j] = cp[j];
 #pragma unroll
           for (int rr = 0; rr < 4; ++rr) {
             if (rr < nrow && !overflow) {
-              const uint32_t xEv = row(eg[rr], XB);
-              int xe = max((int)(xEv & 0xffffu), (int)(xEv >> 16));
-              xe = __reduce_max_sync(0xffffffffu, xe);
+              const uint32_t xEv = row(eg[rr]);
+              int ue = max((int)(xEv & 0xffffu), (int)(xEv >> 16));
+              ue = __reduce_max_sync(0xffffffffu, ue);
+              umax = max(umax, ue);
+              int xe = ue + xB;
               if (xe + bias >= 255) overflow = true;
               else {
                 xe = max(xe - tec, 0);
                 xJ = max(xJ, xe);
-                xB = max(max(base, xJ) - tjbm, 0);
-                XB = (uint32_t)xB * 0x00010001u;
+                const int xBn = max(max(base, xJ) - tjbm, 0);
+                if (xBn != xB) {                              // re-base u on the new xB (xB never decreases)
+                  const uint32_t nd = (uint32_t)(uint16_t)(int16_t)(xB - xBn) * 0x00010001u;
+#pragma unroll
+                  for (int j = 0; j < H; ++j) sv[j] = __viaddmax_s16x2_relu(sv[j], nd, 0x80008000u);
+                  xB = xBn;
+                }
               }
             }
           }
         }
       }
       r16 = rnext;
+    }
+    if (!overflow && umax == 0) {
+      // no positive cell anywhere (never the case for a pair the SSV pre-filter forwards on a positive threshold): the plain
+      // recurrence, row by row, with the exact row maxima of sv
+      xJ = 0; xB = max(base - tjbm, 0);
+#pragma unroll
+      for (int j = 0; j < H; ++j) sv[j] = 0u;
+      for (int i = 0; i < L && !overflow; ++i) {
+        const uint32_t x = p.res[p.off[s] + i];
+        uint32_t e[H];
+#pragma unroll
+        for (int j = 0; j < H; ++j) e[j] = __ldg(rmb + (x * H + j) * 32);
+        const uint32_t XBw = (uint32_t)xB * 0x00010001u;
+        uint32_t up = __shfl_up_sync(0xffffffffu, sv[H - 1], 1);
+        if (lane == 0) up = 0u;
+        const uint32_t in0 = __byte_perm(up, sv[H - 1], 0x5432);
+        uint32_t xEv = 0u;
+#pragma unroll
+        for (int j = H - 1; j >= 1; --j) { sv[j] = __viaddmax_s16x2_relu(__vmaxs2(sv[j - 1], XBw), e[j], 0x80008000u); xEv = __vmaxs2(xEv, sv[j]); }
+        sv[0] = __viaddmax_s16x2_relu(__vmaxs2(in0, XBw), e[0], 0x80008000u);
+        xEv = __vmaxs2(xEv, sv[0]);
+        int xe = max((int)(xEv & 0xffffu), (int)(xEv >> 16));
+        xe = __reduce_max_sync(0xffffffffu, xe);
+        if (xe + bias >= 255) overflow = true;
+        else { xe = max(xe - tec, 0); xJ = max(xJ, xe); xB = max(max(base, xJ) - tjbm, 0); }
+      }
     }
     if (lane == 0) {
       float usc;
