@@ -448,10 +448,10 @@ def main():
                                       "what": "same kernel, one batch in flight (no other stream on the SMs)"},
                          "note": "the stage is DP-cell bound, not HBM bound (SURVEY.md 8d): see gcups"},
             "gcups": {"real_cells_per_step": real_cells, "tile_cells_per_step": cells / args.steps, "ssv_gcups_real": real_cells / ssv_s / 1e9,
-                      "ssv_gcups_tile": cells / args.steps / ssv_s / 1e9, "ssv_gcups_real_isolated": real_cells / (iso_ssv_ms / 1e3) / 1e9, "smem_bound_gcups": 148 * (2048.0 / 35.0) * 1.965,
-                      "smem_bound_note": "J=32 tile row = 8 LDS.128 (32 wavefronts) + 1 SHFL (3) per 2048 cells at 1 wavefront/clk/SM, 148 SMs, 1.965 GHz",
+                      "ssv_gcups_tile": cells / args.steps / ssv_s / 1e9, "ssv_gcups_real_isolated": real_cells / (iso_ssv_ms / 1e3) / 1e9, "smem_bound_gcups": 148 * (2048.0 / 31.0) * 1.965,
+                      "smem_bound_note": "J=32 tile row = 7 LDS.128 (1 int8 chunk + 6 int16 quads = 28 wavefronts) + 1 SHFL (3) per 2048 cells at 1 wavefront/clk/SM, 148 SMs, 1.965 GHz",
                       "ssv_gcups_tile_isolated": cells / args.steps / (iso_ssv_ms / 1e3) / 1e9,
-                      "ssv_frac_of_smem_bound": (cells / args.steps / (iso_ssv_ms / 1e3) / 1e9) / (148 * (2048.0 / 35.0) * 1.965),
+                      "ssv_frac_of_smem_bound": (cells / args.steps / (iso_ssv_ms / 1e3) / 1e9) / (148 * (2048.0 / 31.0) * 1.965),
                       "stage_ms_per_step": {"ssv": ssv_ms / args.steps, "msv_exact": msv_ms / args.steps, "bias+vit+fwd+domdef": other_ms / args.steps,
                                             "wall_ms_per_step": {k_: v_ / args.steps for k_, v_ in host_ms.items()},
                                             "isolated_step": {"ssv": iso_st.ms_ssv, "msv_exact": iso_st.ms_msv, "bias": iso_st.ms_bias, "vit": iso_st.ms_vit, "fwd": iso_st.ms_fwd,

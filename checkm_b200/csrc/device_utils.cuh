@@ -14,6 +14,14 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   return v;
 }
 
+// prmt.b32 with the PTX selector semantics (bit 3 of a selector nibble replicates the sign of the selected byte; the
+// __byte_perm intrinsic masks that bit off)
+__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
 // ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk; SASS: UBLKCP) ----
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -16,7 +16,14 @@ namespace ckm {
 // last cell of the last slot is always padding so nothing leaks into the next model of the tile.
 // Emission table of a tile in HBM/shared memory: int16 [KPAD residues][J/4 quads][32 lanes][4 q][2 halves]
 // i.e. per residue row J*32 32-bit words; lane l reads quad g as one 128-bit load at word (g*32 + l)*4.
+// J = 32 tiles keep the first two quads (words 0..7 of every lane) as int8 pairs in ONE 16-byte chunk per lane
+// (gains clamped at -128, exact while u < 128; the kernel flags any slot that reaches 127): 7 instead of 8 LDS.128 per
+// row, the sign-extending unpack costs one PRMT per word on the ALU pipe, which has the headroom.
 // ------------------------------------------------------------------------------------------------
+constexpr int SSV_I8_WORDS = 8;       // words per lane stored as int8 pairs in J = 32 tiles
+__host__ __device__ constexpr int ssv_row_bytes(int J) { return (J == 32) ? 128 * J - 16 * 32 * (SSV_I8_WORDS / 4 - 1) : 128 * J; }
+__host__ __device__ constexpr int ssv_table_bytes(int J) { return KPAD * ssv_row_bytes(J); }
+__host__ __device__ constexpr int ssv_block_bytes(int J) { return ssv_table_bytes(J) + 768; }
 struct TileModel {       // one model (or one 1024-cell chunk of a long model) inside a tile
   int32_t model;         // database index
   int32_t slot0, nslots;

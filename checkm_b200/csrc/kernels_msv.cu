@@ -22,8 +22,8 @@ namespace ckm {
 // SSV pre-filter
 // ------------------------------------------------------------------------------------------------
 
-template <int J> __host__ __device__ constexpr int tile_table_bytes() { return KPAD * 128 * J; }
-template <int J> __host__ __device__ constexpr int tile_block_bytes() { return KPAD * 128 * J + 768; }
+template <int J> __host__ __device__ constexpr int tile_table_bytes() { return ssv_table_bytes(J); }
+template <int J> __host__ __device__ constexpr int tile_block_bytes() { return ssv_block_bytes(J); }
 
 
 template <int J>
@@ -32,11 +32,19 @@ __device__ __forceinline__ void ssv_rows(const uint8_t *__restrict__ res, int L,
   constexpr int G = J / 4;
   const uint4 *rp = reinterpret_cast<const uint4 *>(res);
   const uint32_t lane_off = tile_smem + lane * 16;
+  constexpr bool I8 = (J == 32);                       // words 0..7 of every lane come as int8 pairs in one 16-byte chunk
+  constexpr int G0 = I8 ? SSV_I8_WORDS / 4 : 0;       // int16 quads start here
   auto do_row = [&](uint32_t x, int i) {
-    const uint32_t row = lane_off + x * (128 * J);
+    const uint32_t row = lane_off + x * ssv_row_bytes(J);
     uint4 e[G];
+    if (I8) {
+      const uint4 c = lds128(row);
+      const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
-    for (int g = 0; g < G; ++g) e[g] = lds128(row + g * 512);
+      for (int q = 0; q < SSV_I8_WORDS; ++q) (&e[q >> 2].x)[q & 3] = prmt_b32(cw[q >> 1], 0u, (q & 1) ? 0xB3A2u : 0x9180u);   // sign-extend a byte pair
+    }
+#pragma unroll
+    for (int g = G0; g < G; ++g) e[g] = lds128(row + (g - (I8 ? G0 - 1 : 0)) * 512);
     uint32_t bndw = 0;
     if (bnd_in != nullptr) bndw = (i > 0) ? (uint32_t)(uint16_t)bnd_in[i - 1] : 0u;      // chained tile: cell 0 continues the previous chunk's last cell
     const uint32_t sh = __shfl_sync(0xffffffffu, u[J - 1], (lane + 31) & 31);
@@ -78,6 +86,7 @@ __global__ void __launch_bounds__(SSV_WARPS * 32, 1) ssv_kernel(SsvParams p) {
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t sel = (lane == 0) ? 0x1054u : 0x3210u;
   constexpr int TB = tile_block_bytes<J>();
+  constexpr int I8CAP = (J == 32) ? 127 : 32767;
   if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
   __syncthreads();
   uint32_t phase = 0;
@@ -142,8 +151,9 @@ __global__ void __launch_bounds__(SSV_WARPS * 32, 1) ssv_kernel(SsvParams p) {
         const int32_t *F = reinterpret_cast<const int32_t *>(meta + 256);
         const int32_t *SM = reinterpret_cast<const int32_t *>(meta + 512);
         const int ulo = (int)(int16_t)(xE & 0xffffu), uhi = (int)(int16_t)(xE >> 16);
-        const int thr_lo = min((int)floorf(A[lane] + Bs) - 1, F[lane] + tjb);
-        const int thr_hi = min((int)floorf(A[32 + lane] + Bs) - 1, F[32 + lane] + tjb);
+        // (J = 32 tiles carry int8 gains clamped at -128: exact while u < 128, so a slot that reached 127 is forwarded too)
+        const int thr_lo = min(min((int)floorf(A[lane] + Bs) - 1, F[lane] + tjb), I8CAP);
+        const int thr_hi = min(min((int)floorf(A[32 + lane] + Bs) - 1, F[32 + lane] + tjb), I8CAP);
         const bool c_lo = (SM[lane] >= 0) && (ulo >= thr_lo);
         const bool c_hi = (SM[32 + lane] >= 0) && (uhi >= thr_hi);
         const unsigned m_lo = __ballot_sync(0xffffffffu, c_lo), m_hi = __ballot_sync(0xffffffffu, c_hi);

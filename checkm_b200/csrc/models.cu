@@ -27,7 +27,7 @@ static int upload(T **dptr, const std::vector<T> &h) {
   return CKM_OK;
 }
 
-static int tile_block_bytes_host(int J) { return KPAD * 128 * J + 768; }
+static int tile_block_bytes_host(int J) { return ssv_block_bytes(J); }
 
 // Packs the models into SSV tiles (see engine.hpp) and builds the int16 emission-delta tables.
 static void build_tiles(ckm_models &db, std::vector<uint8_t> &blob) {
@@ -112,13 +112,23 @@ static void build_tiles(ckm_models &db, std::vector<uint8_t> &blob) {
   for (size_t t = 0; t < tiles.size(); ++t) {
     const int J = tiles[t].J;
     uint8_t *base = blob.data() + db.tiles[t].table_off;
-    int16_t *tab = reinterpret_cast<int16_t *>(base);
-    float *A = reinterpret_cast<float *>(base + KPAD * 128 * J);
-    int32_t *F = reinterpret_cast<int32_t *>(base + KPAD * 128 * J + 256);
-    int32_t *SM = reinterpret_cast<int32_t *>(base + KPAD * 128 * J + 512);
+    const bool i8 = (J == 32);
+    const int RB = ssv_row_bytes(J);
+    float *A = reinterpret_cast<float *>(base + ssv_table_bytes(J));
+    int32_t *F = reinterpret_cast<int32_t *>(base + ssv_table_bytes(J) + 256);
+    int32_t *SM = reinterpret_cast<int32_t *>(base + ssv_table_bytes(J) + 512);
     for (int s = 0; s < 64; ++s) { A[s] = 1e30f; F[s] = 1 << 28; SM[s] = -1; }
+    // where the gain of cell (lane, half, q) for residue x lives, and a store that knows the cell's width
+    auto put = [&](int x, int lane, int half, int q, int d) {
+      uint8_t *row = base + (size_t)x * RB;
+      if (i8 && q < SSV_I8_WORDS) reinterpret_cast<int8_t *>(row)[lane * 16 + 2 * q + half] = (int8_t)std::max(d, -128);
+      else {
+        const int g = (q >> 2) - (i8 ? (SSV_I8_WORDS / 4 - 1) : 0);      // 16-byte chunk index inside the row
+        reinterpret_cast<int16_t *>(row + ((size_t)g * 32 + lane) * 16)[(q & 3) * 2 + half] = (int16_t)std::max(d, -32768);
+      }
+    };
     // default: padding everywhere
-    for (size_t i = 0; i < (size_t)KPAD * 64 * J; ++i) tab[i] = -32768;
+    for (int x = 0; x < KPAD; ++x) for (int lane = 0; lane < 32; ++lane) for (int half = 0; half < 2; ++half) for (int q = 0; q < J; ++q) put(x, lane, half, q, -32768);
     for (size_t j = 0; j < tiles[t].tm.size(); ++j) {
       const TileModel &tm = tiles[t].tm[j];
       const Model &m = db.models[tm.model];
@@ -132,10 +142,7 @@ static void build_tiles(ckm_models &db, std::vector<uint8_t> &blob) {
           const int k = tm.chunk * 64 * J + sl * J + q + 1;    // model position of this cell
           if (k > m.M) continue;
           for (int x = 0; x < KP; ++x) {
-            const int d = (int)m.bias_b - (int)m.rbv[(size_t)x * W1 + k];
-            // word index inside residue row x: ((q/4)*32 + lane)*4 + (q%4); halves interleaved
-            const size_t w = (size_t)x * (J * 32) + ((size_t)(q >> 2) * 32 + lane) * 4 + (q & 3);
-            tab[w * 2 + half] = (int16_t)d;
+            put(x, lane, half, q, (int)m.bias_b - (int)m.rbv[(size_t)x * W1 + k]);
           }
         }
       }
@@ -145,8 +152,8 @@ static void build_tiles(ckm_models &db, std::vector<uint8_t> &blob) {
   for (size_t t = 0; t < tiles.size(); ++t) {
     const int J = tiles[t].J;
     uint8_t *base = blob.data() + db.tiles[t].table_off;
-    float *A = reinterpret_cast<float *>(base + KPAD * 128 * J);
-    int32_t *F = reinterpret_cast<int32_t *>(base + KPAD * 128 * J + 256);
+    float *A = reinterpret_cast<float *>(base + ssv_table_bytes(J));
+    int32_t *F = reinterpret_cast<int32_t *>(base + ssv_table_bytes(J) + 256);
     for (auto &tm : tiles[t].tm) {
       const Model &m = db.models[tm.model];
       const double F1 = 0.02;
