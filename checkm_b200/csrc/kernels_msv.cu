@@ -231,7 +231,7 @@ int launch_ssv(int J, const SsvParams &p, int grid, size_t smem_bytes, cudaStrea
 
 
 __global__ void __launch_bounds__(MSV_WARPS * 32) msv_exact_kernel(MsvParams p) {
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint8_t *row0 = smem + (size_t)warp * 2 * p.row_bytes, *row1 = row0 + p.row_bytes;
   const int ncand = min(*p.cand_count, p.cand_cap);

@@ -391,7 +391,6 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
   const int nsm = e->prop.multiProcessorCount;
   DevBuf dpairs, dxf, dxb, dvec, dregions, denvs, ddoms, dhits, dscratch, dtbl, dporder, deorder;
   std::vector<DomainOut> doms; std::vector<HitOut> hout((size_t)npairs);
-  std::vector<Envelope> envs;
   CKM_CUDA(cudaEventRecord(e->ev[6], st));
   tr.mark("pair list sorted");
   if (npairs > 0) {
