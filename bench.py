@@ -74,7 +74,7 @@ def model_db(tag=''):
 
 
 def make_bins(plant_path, n, seed0):
-    from checkm_b200 import synth
+    from tools import synth
     hm = synth.read_hmms(plant_path)
     bins = [synth.make_bin('bin%d' % (seed0 + i), hm, seed=seed0 + i, n_orfs=ORFS_PER_BIN, copies=(0, 1, 1, 1, 2)) for i in range(n)]
     res = np.concatenate([b.residues for b in bins])

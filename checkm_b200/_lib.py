@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libckm.so")
+LIB_PATH = os.environ.get("CKM_LIBRARY") or os.path.join(_HERE, "libckm.so")     # CKM_LIBRARY: an experimental build of the same library
 
 
 class ModelInfo(C.Structure):

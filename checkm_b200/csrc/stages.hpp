@@ -4,7 +4,10 @@
 
 namespace ckm {
 
-constexpr int SSV_WARPS = 16;
+#ifndef CKM_SSV_WARPS
+#define CKM_SSV_WARPS 16
+#endif
+constexpr int SSV_WARPS = CKM_SSV_WARPS;
 constexpr int SSV_WARPS_HOST = SSV_WARPS;
 constexpr int MSV_WARPS = 8;
 

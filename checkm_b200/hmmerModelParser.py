@@ -10,7 +10,7 @@ class HmmModelError(Exception):
     pass
 
 
-class HmmModel(object):
+class _HmmModel(object):
     """Plain attribute bag: ga/tc/nc default to None, acc defaults to name when no ACC key was seen."""
 
     def __init__(self, keys):
@@ -21,6 +21,14 @@ class HmmModel(object):
             self.acc = keys['name']
         for key, value in keys.items():
             setattr(self, key, value)
+
+
+try:                                    # drop-in inside a CheckM install: use CheckM's own class, so that the pickles
+    from checkm.hmmerModelParser import HmmModel      # (storage/checkm_hmm_info.pkl.gz, markerSets.py:524-540) are interchangeable
+except Exception:                       # stand-alone: same attributes, our module path
+    HmmModel = _HmmModel
+    HmmModel.__name__ = 'HmmModel'
+    HmmModel.__qualname__ = 'HmmModel'
 
 
 def _cutoff_pair(text):

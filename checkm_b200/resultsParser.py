@@ -474,27 +474,27 @@ class ResultsParser(object):
 
 
 def _make_pretty_table(header):
-    """CheckM's vendored prettytable when CheckM is installed, else a plain fixed-width table with the same calls."""
-    try:
-        import checkm.prettytable as prettytable
-        t = prettytable.PrettyTable(header)
-        t.float_format = '.2'
-        t.align = 'c'
-        t.align[header[0]] = 'l'
-        t.hrules = prettytable.FRAME
-        t.vrules = prettytable.NONE
-        return t
-    except Exception:
-        return _PlainTable(header)
+    return _FrameTable(header)
 
 
-class _PlainTable(object):
+class _FrameTable(object):
+    """The one table style CheckM prints (resultsParser.py:246-252: centred cells, first column left-aligned, floats as
+    %.2f, a rule of dashes above and below the header and at the bottom, no vertical rules), with the calls its callers
+    make: add_row, get_string(sortby=, reversesort=, print_empty=).  Cells are framed as the vendored table class frames
+    them when vertical rules are off: a blank where each rule would be plus one blank of padding either side."""
+
     def __init__(self, header):
         self.header = list(header)
         self.rows = []
 
     def add_row(self, row):
+        if len(row) != len(self.header):
+            raise Exception("Row has incorrect number of values, (actual) %d!=%d (expected)" % (len(row), len(self.header)))
         self.rows.append(list(row))
+
+    @staticmethod
+    def _cell(v):
+        return ('%.2f' % v) if isinstance(v, float) else str(v)
 
     def get_string(self, sortby=None, reversesort=False, print_empty=True):
         if not self.rows and not print_empty:
@@ -502,13 +502,21 @@ class _PlainTable(object):
         rows = self.rows
         if sortby is not None:
             i = self.header.index(sortby)
-            rows = sorted(rows, key=lambda r: r[i], reverse=reversesort)
-        cells = [[('%.2f' % v) if isinstance(v, float) else str(v) for v in r] for r in rows]
+            rows = sorted(rows, key=lambda r: [r[i]] + r, reverse=reversesort)      # ties fall through to the whole row
+        cells = [[self._cell(v) for v in r] for r in rows]
         widths = [max([len(h)] + [len(c[i]) for c in cells]) for i, h in enumerate(self.header)]
-        rule = '-' * (sum(widths) + 2 * len(widths))
-        lines = [rule, '  '.join(h.ljust(w) if i == 0 else h.center(w) for i, (h, w) in enumerate(zip(self.header, widths))), rule]
+        rule = '-' * (sum(widths) + 3 * len(widths) + 1)
+
+        def line(values):
+            out = [' ']
+            for i, (v, w) in enumerate(zip(values, widths)):
+                out.append(' ' + (v.ljust(w) if i == 0 else v.center(w)) + ' ')
+                out.append(' ')
+            return ''.join(out)
+
+        lines = [rule, line(self.header), rule]
         for c in cells:
-            lines.append('  '.join(v.ljust(w) if i == 0 else v.center(w) for i, (v, w) in enumerate(zip(c, widths))))
+            lines.append(line(c))
         lines.append(rule)
         return '\n'.join(lines)
 

@@ -1458,6 +1458,54 @@ int orc_results_nhits(const orc_results *r) { return r->nhits; }
 const orc_hit *orc_results_hit(const orc_results *r, int i) { return &r->hits[i]; }
 const orc_domain *orc_hit_domain(const orc_hit *h, int d) { return &h->dcl[d]; }
 
+/* Raw filter scores (nats) of every (model, sequence) pair, for the calibration tests: msv / vit / fwd are
+ * [nmodels*nseq] or NULL.  No thresholds are applied; an MSV/Viterbi overflow is reported as +inf. */
+typedef struct {
+  orc_profile **profs; int nmodels;
+  const uint8_t *residues; const int64_t *offsets; int nseq;
+  float *msv, *vit, *fwd;
+  long next; pthread_mutex_t mu;
+} stage_ctx;
+
+static void *stage_worker(void *arg)
+{
+  stage_ctx *c = (stage_ctx *)arg;
+  const long chunk = 32, total = (long)c->nmodels * c->nseq;
+  while (1) {
+    pthread_mutex_lock(&c->mu);
+    long begin = c->next; c->next += chunk;
+    pthread_mutex_unlock(&c->mu);
+    if (begin >= total) break;
+    long end = begin + chunk; if (end > total) end = total;
+    for (long w = begin; w < end; w++) {
+      int m = (int)(w / c->nseq), s = (int)(w % c->nseq);
+      int L = (int)(c->offsets[s + 1] - c->offsets[s]);
+      const uint8_t *dsq = c->residues + c->offsets[s];
+      int xj;
+      if (c->msv) orc_msv(c->profs[m], dsq, L, &c->msv[w], &xj);
+      if (c->vit) orc_vitfilter(c->profs[m], dsq, L, &c->vit[w]);
+      if (c->fwd) orc_forward_parser(c->profs[m], dsq, L, &c->fwd[w]);
+    }
+  }
+  return NULL;
+}
+
+int orc_stage_scores(orc_profile **profs, int nmodels, const uint8_t *residues, const int64_t *offsets, int nseq,
+                     float *msv, float *vit, float *fwd, int nthreads)
+{
+  stage_ctx c; memset(&c, 0, sizeof(c));
+  c.profs = profs; c.nmodels = nmodels; c.residues = residues; c.offsets = offsets; c.nseq = nseq;
+  c.msv = msv; c.vit = vit; c.fwd = fwd;
+  pthread_mutex_init(&c.mu, NULL);
+  if (nthreads < 1) nthreads = 1;
+  pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
+  for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, stage_worker, &c);
+  for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+  free(th);
+  pthread_mutex_destroy(&c.mu);
+  return 0;
+}
+
 /* domtblout: one row per reported domain of each reported target */
 int orc_write_domtblout(const orc_results *r, orc_profile **profs, const char **seqnames, const char **seqdescs, const char *path)
 {

@@ -138,6 +138,10 @@ int  orc_results_nhits(const orc_results *r);
 const orc_hit *orc_results_hit(const orc_results *r, int i);
 const orc_domain *orc_hit_domain(const orc_hit *h, int d);
 
+/* raw filter scores (nats) of every (model, sequence) pair -- calibration tests; each output is [nmodels*nseq] or NULL */
+int orc_stage_scores(orc_profile **profs, int nmodels, const uint8_t *residues, const int64_t *offsets, int nseq,
+                     float *msv, float *vit, float *fwd, int nthreads);
+
 /* domtblout text for one search (names/descriptions supplied by the caller) */
 int orc_write_domtblout(const orc_results *r, orc_profile **profs,
                         const char **seqnames, const char **seqdescs, const char *path);

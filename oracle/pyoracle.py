@@ -72,6 +72,8 @@ def lib():
         L.orc_write_domtblout.argtypes = [C.POINTER(Results), C.POINTER(C.c_void_p), C.POINTER(C.c_char_p),
                                           C.POINTER(C.c_char_p), C.c_char_p]
         L.orc_digitize.argtypes = [C.c_char_p, C.c_int, C.c_void_p]
+        L.orc_stage_scores.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_int]
         _LIB = L
     return _LIB
 
@@ -157,6 +159,19 @@ def msv(hf, m, dsq):
 def ssv_xe(hf, m, dsq):
     d = np.ascontiguousarray(dsq, dtype=np.uint8)
     return lib().orc_ssv_xe(hf.prof_ptrs[m], d.ctypes.data, len(d))
+
+
+def stage_scores(hf, residues, offsets, models=None, msv=True, vit=True, fwd=True, nthreads=1):
+    """Raw MSV / Viterbi / Forward filter scores (nats) of every (model, sequence) pair: dict of [nmodels, nseq] arrays."""
+    res = np.ascontiguousarray(residues, dtype=np.uint8)
+    off = np.ascontiguousarray(offsets, dtype=np.int64)
+    arr = hf.prof_array(models)
+    n = len(off) - 1
+    out = {k: np.empty((len(arr), n), dtype=np.float32) for k, on in (('msv', msv), ('vit', vit), ('fwd', fwd)) if on}
+    lib().orc_stage_scores(arr, len(arr), res.ctypes.data, off.ctypes.data, n,
+                           out['msv'].ctypes.data if msv else None, out['vit'].ctypes.data if vit else None,
+                           out['fwd'].ctypes.data if fwd else None, nthreads)
+    return out
 
 
 def search(hf, residues, offsets, E=0.1, domE=0.1, nthreads=1, models=None):

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import pyoracle as po          # noqa: E402
-from checkm_b200 import synth              # noqa: E402
+from tools import synth              # noqa: E402
 
 CPR = os.path.join(HERE, 'cpr_43_markers.hmm')
 

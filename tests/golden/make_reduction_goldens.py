@@ -137,7 +137,7 @@ def main():
     cases = {'kat1': {'binA': KAT1}, 'kat2': {'binB': KAT2}}
     # oracle-written tables for synthetic bins
     from oracle import pyoracle as po
-    from checkm_b200 import synth
+    from tools import synth
     hf = po.HmmFile(CPR)
     hm = synth.read_hmms(CPR)
     synth_tables = {}

@@ -4,7 +4,7 @@ Forward scores within 1e-3 bits (north_star tolerance; fp32 summation order diff
 import numpy as np
 import pytest
 
-from checkm_b200 import synth
+from tools import synth
 from conftest import CPR_HMM
 
 pytestmark = pytest.mark.gpu

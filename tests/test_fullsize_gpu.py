@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 import bench
-from checkm_b200 import synth
+from tools import synth
 
 pytestmark = pytest.mark.gpu
 

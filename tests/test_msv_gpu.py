@@ -4,7 +4,7 @@ the oracle's xJ byte, and every pair the GPU scores must agree with the oracle."
 import numpy as np
 import pytest
 
-from checkm_b200 import synth
+from tools import synth
 from conftest import CPR_HMM
 
 pytestmark = pytest.mark.gpu

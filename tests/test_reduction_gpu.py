@@ -76,7 +76,7 @@ def test_sidecar_equals_text_path(engine, setup, tmp_path):
     """Search -> domtblout + side-car; the reduction must give the same table from either."""
     import shutil
     import numpy as np
-    from checkm_b200 import synth
+    from tools import synth
     from checkm_b200.hmmer import HMMERRunner
     from checkm_b200.resultsParser import ResultsParser
     hm = synth.read_hmms(CPR_HMM)

@@ -4,7 +4,7 @@ Hit table rows (target, query, domain index, hmm/ali/env coordinates) must be id
 import numpy as np
 import pytest
 
-from checkm_b200 import synth
+from tools import synth
 from conftest import CPR_HMM
 
 pytestmark = pytest.mark.gpu

@@ -1,0 +1,88 @@
+"""Text-level parity: the domtblout file is what CheckM consumes (checkm/hmmer.py:184-200 re-parses the "%6.1f" / "%9.2g"
+strings and resultsParser.py:356-367 compares them with the GA/TC/NC cutoffs), so the GPU's printed rows must equal the
+oracle's printed rows -- not merely agree within a float tolerance.  Every bin below is searched on the device
+(ckm_search -> ckm_write_domtblout) and by the oracle (orc_search -> orc_write_domtblout); the data lines are compared
+field by field as text, and the float columns additionally at the north-star tolerance of 1e-3 bits, flat.
+The mismatch count is printed; the bar is 0."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CPR_HMM
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+TOL_BITS = 1e-3
+
+
+def _data_lines(path):
+    return [l.rstrip('\n') for l in open(path) if l.strip() and not l.startswith('#')]
+
+
+def _both_tables(engine, models, ohf, oracle, b, tmp_path, tag, model_idx=None):
+    from checkm_b200.hmmer import write_domtblout
+    db = engine.seqdb(b.residues, b.offsets)
+    hits = engine.search(models, db, model_idx=model_idx)
+    db.close()
+    gpath, opath = str(tmp_path / (tag + '.gpu.txt')), str(tmp_path / (tag + '.orc.txt'))
+    write_domtblout(models, hits, 0, 0, b.names, b.descs, gpath)
+    rp = oracle.search(ohf, b.residues, b.offsets, nthreads=os.cpu_count() or 8, models=model_idx)
+    rows = oracle.hits_table(rp)
+    oracle.write_domtblout(rp, ohf, b.names, b.descs, opath, models=model_idx)
+    oracle.free_results(rp)
+    return _data_lines(gpath), _data_lines(opath), hits, rows
+
+
+def _compare(glines, olines, hits, rows, tag, stats):
+    assert len(glines) == len(olines) == len(hits) == len(rows), (tag, len(glines), len(olines))
+    bad = []
+    for g, o in zip(glines, olines):
+        gf, of = g.split(), o.split()
+        if gf != of:
+            bad.append((g, o))
+    worst = 0.0
+    for r, h in zip(rows, hits):
+        for a, b in ((r['full_score'], h['full_score']), (r['dom_score'], h['dom_score']), (r['full_bias'], h['full_bias']), (r['dom_bias'], h['dom_bias'])):
+            d = abs(float(a) - float(b))
+            worst = max(worst, d)
+            stats.append(d)
+            assert d <= TOL_BITS, (tag, r, h)
+        assert abs(float(r['acc']) - float(h['acc'])) <= 1e-4
+    print('%s: %d rows, %d differ as text, worst score/bias difference %.3g bits' % (tag, len(glines), len(bad), worst))
+    return bad
+
+
+CASES = [('single', 31, dict(n_orfs=300, max_len=1200)),
+         ('tandem', 32, dict(n_orfs=200, tandem_prob=0.5, max_len=1500)),
+         ('split', 36, dict(n_orfs=260, split_prob=0.5, max_len=900, tandem_prob=0.1)),
+         ('sharp', 37, dict(n_orfs=240, sharpen=0.5, max_len=2000, tandem_prob=0.2, copies=(1, 1, 2, 3))),
+         ('degenerate', 38, dict(n_orfs=200, degenerate_prob=0.03, max_len=800))]
+
+
+def test_domtblout_text_identical(engine, cpr_models, cpr_oracle, oracle, tmp_path):
+    hm = synth.read_hmms(CPR_HMM)
+    stats, bad = [], []
+    for tag, seed, kw in CASES:
+        b = synth.make_bin(tag, hm, seed=seed, **kw)
+        g, o, hits, rows = _both_tables(engine, cpr_models, cpr_oracle, oracle, b, tmp_path, tag)
+        assert len(g) >= 20
+        bad += _compare(g, o, hits, rows, tag, stats)
+    s = np.asarray(stats)
+    print('all cases: %d float fields, median |diff| %.3g, 99%% %.3g, max %.3g bits; text mismatches %d' %
+          (len(s), np.median(s), np.quantile(s, 0.99), s.max(), len(bad)))
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    if os.path.isdir(out):
+        np.save(os.path.join(out, 'text_parity_diffs.npy'), s)
+    assert not bad, bad[:3]
+
+
+def test_domtblout_text_identical_full_bin(engine, cpr_models, cpr_oracle, oracle, tmp_path):
+    """One full-size bin (BASELINE.json configs[1]: 2 Mb, 1,900 ORFs) x the 43 base models, every row as text."""
+    hm = synth.read_hmms(CPR_HMM)
+    b = synth.make_bin('full', hm, seed=2024, n_orfs=1900, tandem_prob=0.05)
+    g, o, hits, rows = _both_tables(engine, cpr_models, cpr_oracle, oracle, b, tmp_path, 'full')
+    stats = []
+    bad = _compare(g, o, hits, rows, 'full 1,900-ORF bin', stats)
+    assert len(g) >= 40
+    assert not bad, bad[:3]

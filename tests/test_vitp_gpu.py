@@ -12,7 +12,7 @@ What the cases are for (the guard conditions in the header of kernels_vitp.cu):
 import numpy as np
 import pytest
 
-from checkm_b200 import synth
+from tools import synth
 from conftest import CPR_HMM
 
 pytestmark = pytest.mark.gpu

@@ -1,4 +1,4 @@
-"""Seeded synthetic workloads for tests and bench.py.
+"""TEST + BENCH INFRASTRUCTURE (not product). Seeded synthetic workloads for tests and bench.py.
 
 Not part of the search path: it only manufactures inputs -- protein bins in Prodigal naming
 (`>c<j>_<k> # start # end # strand # ID=j_k`, sequences ending in '*') whose ORFs are background
@@ -71,8 +71,10 @@ def read_hmms(path):
     return models
 
 
-def emit_homolog(hmm, rng, k_from=1, k_to=None):
-    """Sample one path through match/insert/delete states k_from..k_to of the core model; returns residue codes."""
+def emit_homolog(hmm, rng, k_from=1, k_to=None, sharpen=0.0):
+    """Sample one path through match/insert/delete states k_from..k_to of the core model; returns residue codes.
+    sharpen > 0: a match state emits its consensus residue with that probability (closer homologs; the default 0 draws
+    nothing extra, so seeded bins made without it are unchanged)."""
     k_to = hmm.M if k_to is None else k_to
     out = []
     k = k_from
@@ -80,7 +82,10 @@ def emit_homolog(hmm, rng, k_from=1, k_to=None):
     while True:
         if state == 'M':
             p = hmm.mat[k] / hmm.mat[k].sum()
-            out.append(rng.choice(20, p=p))
+            if sharpen > 0.0 and rng.random() < sharpen:
+                out.append(int(np.argmax(p)))
+            else:
+                out.append(rng.choice(20, p=p))
         elif state == 'I':
             p = hmm.ins[k] / hmm.ins[k].sum()
             out.append(rng.choice(20, p=p))
@@ -135,7 +140,7 @@ class Bin:
 
 
 def make_bin(bin_id, hmms, seed, n_orfs=1900, mean_len=310, copies=(0, 1, 1, 1, 2), split_prob=0.08,
-             orfs_per_contig=40, degenerate_prob=0.002, tandem_prob=0.0, max_len=3000):
+             orfs_per_contig=40, degenerate_prob=0.002, tandem_prob=0.0, max_len=3000, sharpen=0.0):
     """Build one bin: background ORFs, 0-2 planted copies of every family, some split
     across adjacent ORFs (k, k+1 of one contig) to exercise the adjacent-ORF merge, a sprinkle of X/B/Z."""
     rng = np.random.default_rng(seed)
@@ -159,16 +164,16 @@ def make_bin(bin_id, hmms, seed, n_orfs=1900, mean_len=310, copies=(0, 1, 1, 1, 
             o = take()
             if rng.random() < split_prob and h.M >= 60:
                 cut = int(rng.integers(h.M // 3, 2 * h.M // 3))
-                a = emit_homolog(h, rng, 1, cut)
-                b = emit_homolog(h, rng, cut + 1, h.M)
+                a = emit_homolog(h, rng, 1, cut, sharpen)
+                b = emit_homolog(h, rng, cut + 1, h.M, sharpen)
                 for orf, frag in ((o, a), (o + 1, b)):
                     lf, rf = int(rng.integers(5, 60)), int(rng.integers(5, 60))
                     seqs[orf] = np.concatenate([rng.choice(20, size=lf, p=BG), frag, rng.choice(20, size=rf, p=BG)]).astype(np.uint8)
                 planted.append((mi, o, 'split'))
             else:
-                frag = emit_homolog(h, rng)
+                frag = emit_homolog(h, rng, sharpen=sharpen)
                 if rng.random() < tandem_prob:
-                    frag = np.concatenate([frag, rng.choice(20, size=int(rng.integers(3, 15)), p=BG), emit_homolog(h, rng)])
+                    frag = np.concatenate([frag, rng.choice(20, size=int(rng.integers(3, 15)), p=BG), emit_homolog(h, rng, sharpen=sharpen)])
                 lf, rf = int(rng.integers(0, 120)), int(rng.integers(0, 120))
                 seqs[o] = np.concatenate([rng.choice(20, size=lf, p=BG), frag, rng.choice(20, size=rf, p=BG)]).astype(np.uint8)
                 planted.append((mi, o, 'full'))
