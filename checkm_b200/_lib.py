@@ -31,7 +31,7 @@ class Stats(C.Structure):
                 ("n_hits_seq", C.c_int64), ("n_domains", C.c_int64), ("n_reported", C.c_int64),
                 ("ms_ssv", C.c_float), ("ms_msv", C.c_float), ("ms_bias", C.c_float), ("ms_vit", C.c_float),
                 ("ms_fwd", C.c_float), ("ms_domdef", C.c_float), ("ms_total", C.c_float),
-                ("kernel_launches", C.c_int64), ("n_vit_redo", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("n_vit_redo", C.c_int64), ("n_queue_retries", C.c_int64)]
 
 
 class QaRow(C.Structure):

@@ -143,7 +143,11 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) envelope_kernel(DomdefParams p
         null2[20] = 1.0f; null2[27] = 1.0f; null2[28] = 1.0f; null2[29] = 1.0f;
       }
       __syncwarp();
-      for (int pos = env.i + lane; pos <= env.j; pos += 32) n2sc[pos] = logf(null2[res[pos - env.i]]);
+      // per-residue log ratios: 30 table entries, logarithm in double and rounded once (the float value does not depend on
+      // the libm at hand, so the oracle's host arithmetic reproduces it)
+      if (lane < KPAD) null2[lane] = (float)log((double)null2[lane]);
+      __syncwarp();
+      for (int pos = env.i + lane; pos <= env.j; pos += 32) n2sc[pos] = null2[res[pos - env.i]];
       __syncwarp();
     }
     // ---- optimal accuracy fill: OA matrix overwrites the Forward matrix, specials go to xo ----

@@ -319,8 +319,9 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) ensemble_kernel(EnsembleParams
       nsp = __shfl_sync(0xffffffffu, nsp, 0);
       __syncwarp();
     }
+    const bool sp_overflow = nsp > SPCAP;          // more sampled segments than the clustering buffers hold
     nsp = min(nsp, SPCAP);
-    for (int pos = reg.i + lane; pos <= reg.j; pos += 32) n2sc[pos] = logf(__fdiv_rn(acc[pos - reg.i + 1], (float)NSAMPLES));
+    for (int pos = reg.i + lane; pos <= reg.j; pos += 32) n2sc[pos] = (float)log((double)__fdiv_rn(acc[pos - reg.i + 1], (float)NSAMPLES));
     // ---- single-linkage clustering, numbering the clusters exactly as the sequential reference does: seed = last
     // available vertex; pop a vertex, sweep the available list from the top, move every linked vertex to the stack
     // (filling its hole with the list's last element).  The link tests of a sweep run 32 at a time across the lanes;
@@ -376,11 +377,14 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) ensemble_kernel(EnsembleParams
         for (int h = 0; h < nsp; ++h) if (assign[h] == c) epc[spb[h * 5 + 2] - jmin]++;
         for (cmv = 0, best_j = jmax; best_j >= jmin; --best_j) { cmv += epc[best_j - jmin]; if ((float)cmv / (float)ninc >= 0.02f) break; }
         if (best_i > best_j) continue;
-        if (nout < MAXENV) { eo[nout].pair = reg.pair; eo[nout].i = best_i; eo[nout].j = best_j; eo[nout].null2_done = 1; eo[nout].scratch_off = 0; eo[nout].slot = 0; eo[nout].pad = 0; nout++; }
+        if (nout < MAXENV) { eo[nout].pair = reg.pair; eo[nout].i = best_i; eo[nout].j = best_j; eo[nout].null2_done = 1; eo[nout].scratch_off = 0; eo[nout].slot = 0; eo[nout].pad = 0; }
+        nout++;                          // counted past MAXENV: the host refuses the search rather than drop envelopes silently
       }
+      const int nsig = nout;
+      nout = min(nout, MAXENV);
       // order of occurrence in the target
       for (int a = 1; a < nout; ++a) { Envelope v = eo[a]; int b = a - 1; while (b >= 0 && eo[b].i > v.i) { eo[b + 1] = eo[b]; --b; } eo[b + 1] = v; }
-      ep.env_count[ri] = nout;
+      ep.env_count[ri] = sp_overflow ? -1 : nsig;
     }
     __syncwarp();
   }
@@ -435,13 +439,21 @@ int ensembles_launch(ckm_engine *e, const ckm_models *m, DomdefParams &p, const 
 
 int ensembles_collect(EnsembleJob *job, cudaStream_t st, std::vector<std::vector<Envelope>> &out) {
   cudaError_t err = cudaStreamSynchronize(st);
+  int over = 0;
   if (err == cudaSuccess) {
     out.assign((size_t)job->nm, {});
-    for (int i = 0; i < job->nm; ++i)
-      for (int c = 0; c < job->cnt[i] && c < MAXENV; ++c) out[i].push_back(job->envs[(size_t)i * MAXENV + c]);
+    for (int i = 0; i < job->nm; ++i) {
+      if (job->cnt[i] < 0 || job->cnt[i] > MAXENV) { over++; continue; }
+      for (int c = 0; c < job->cnt[i]; ++c) out[i].push_back(job->envs[(size_t)i * MAXENV + c]);
+    }
   }
   delete job;
-  return err == cudaSuccess ? CKM_OK : cuda_fail(err, "ensemble job");
+  if (err != cudaSuccess) return cuda_fail(err, "ensemble job");
+  if (over) {      // hmmsearch would report every domain; refusing is better than a shorter table
+    set_error("a multi-domain region resolves into more than 32 domains (or 4096 sampled segments): beyond the engine's per-region capacity");
+    return CKM_ECAPACITY;
+  }
+  return CKM_OK;
 }
 void ensembles_abandon(EnsembleJob *job, cudaStream_t st) { if (job) { cudaStreamSynchronize(st); delete job; } }
 

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) vit_kernel(FilterParams p) {
     Candidate cd = p.in[c];
     const int s = cd.seq, m = cd.model, L = p.len[s];
     const ModelScalars ms = p.ms[m];
-    if (ms.vq != 0) continue;               // handled by vit2_kernel<Q>
+    if (p.use_blk && ms.vq != 0) continue;  // handled by vit2_kernel<Q> (CKM_BLK=0 sends every model here)
     bool pass = true;
     if (cd.P > p.F2) {
       const int M = ms.M, nchunk = (M + 31) >> 5;

@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(MSV_WARPS * 32) msv_exact_kernel(MsvParams p) 
     const int2 pr = p.cand[c];
     const int s = pr.x, m = pr.y;
     const ModelScalars ms = p.ms[m];
-    if (ms.msv2_ok) continue;               // handled by msv2_kernel<Q>
+    if (p.use_blk && ms.msv2_ok) continue;  // handled by msv2_kernel<Q> (CKM_BLK=0 sends every model here)
     const int M = ms.M, L = p.len[s];
     const uint8_t *res = p.res + p.off[s];
     const uint8_t *rbv = p.rbv + (int64_t)ms.off_cells * KPAD;

@@ -83,12 +83,22 @@ struct Stage1 {
   int32_t cand_cap = 0, pass_cap = 0;
 };
 
+// Queue capacities: a fraction of the pairs (SSV forwards ~3%, exact MSV keeps ~2%; 1/6 and 1/12 leave a wide margin), all in
+// 64-bit arithmetic, never beyond QUEUE_MAX entries.  `attempt` > 0 is a retry after an overflow: the fractions grow 8-fold
+// each time, so the third attempt holds every pair (or QUEUE_MAX of them).
+constexpr int64_t QUEUE_MAX = (int64_t)1 << 30;
+static int32_t queue_cap(int64_t n_pairs, int64_t divisor, int attempt) {
+  int64_t want = n_pairs / divisor + 65536;
+  for (int a = 0; a < attempt && want < n_pairs; ++a) want *= 8;
+  return (int32_t)std::min<int64_t>(std::min<int64_t>(n_pairs, QUEUE_MAX), std::max<int64_t>((int64_t)1 << 16, want));
+}
+
 static int run_stage1(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, ActiveMasks &am, int64_t n_pairs,
-                      Stage1 &s1, int32_t *xj_dense) {
+                      Stage1 &s1, int32_t *xj_dense, int attempt = 0) {
   cudaStream_t st = e->stream;
   int rc;
-  s1.cand_cap = (int32_t)std::min<int64_t>(n_pairs, std::max<int64_t>(1 << 16, n_pairs / 6 + 65536));
-  s1.pass_cap = (int32_t)std::min<int64_t>(n_pairs, std::max<int64_t>(1 << 16, n_pairs / 12 + 65536));
+  s1.cand_cap = queue_cap(n_pairs, 6, attempt);
+  s1.pass_cap = queue_cap(n_pairs, 12, attempt);
   if ((rc = s1.cand.alloc(sizeof(int2) * (size_t)s1.cand_cap))) return rc;
   if ((rc = s1.pass.alloc(sizeof(Candidate) * (size_t)s1.pass_cap))) return rc;
   if ((rc = s1.cells.alloc(sizeof(unsigned long long)))) return rc;
@@ -148,11 +158,12 @@ static int run_stage1(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
     p.xj_dense = xj_dense; p.model_slot = am.model_slot.as<int32_t>(); p.nseq = db->nseq;
     p.row_bytes = (m->maxM + 2 + 15) / 16 * 16;
     p.F1 = 0.02;
+    p.use_blk = use_blocked_kernels() ? 1 : 0;
     if ((rc = fan_out(e))) return rc;
-    for (int c = 0; c < N_BLK_CLASSES; ++c) if ((rc = launch_msv2(p, c, nsm * 16, e->cls[c]))) return rc;
+    if (p.use_blk) { for (int c = 0; c < N_BLK_CLASSES; ++c) if ((rc = launch_msv2(p, c, nsm * 16, e->cls[c]))) return rc; }
     if ((rc = launch_msv_exact(p, nsm * 4, e->cls[N_BLK_CLASSES]))) return rc;
     if ((rc = fan_in(e))) return rc;
-    e->stats.kernel_launches += 1 + N_BLK_CLASSES;
+    e->stats.kernel_launches += 1 + (p.use_blk ? N_BLK_CLASSES : 0);
   }
   CKM_CUDA(cudaEventRecord(e->ev[2], st));
   return CKM_OK;
@@ -205,8 +216,8 @@ static int run_stage2(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
     e->stats.kernel_launches += N_BLK_CLASSES;
   }
   if ((rc = fan_out(e))) return rc;
-  for (int c = 0; c < N_BLK_CLASSES; ++c) if ((rc = launch_vit2(p, c, nsm * 8, e->cls[c]))) return rc;      // lane-blocked register kernels, one per class
-  if ((rc = launch_vit(p, nsm * 4, e->cls[N_BLK_CLASSES]))) return rc;                                      // models beyond the classes: shared-memory rows
+  if (p.use_blk) { for (int c = 0; c < N_BLK_CLASSES; ++c) if ((rc = launch_vit2(p, c, nsm * 8, e->cls[c]))) return rc; }   // lane-blocked register kernels, one per class
+  if ((rc = launch_vit(p, nsm * 4, e->cls[N_BLK_CLASSES]))) return rc;                                      // models beyond the classes (all models when CKM_BLK=0): shared-memory rows
   if ((rc = fan_in(e))) return rc;
   CKM_CUDA(cudaEventRecord(e->ev[4], st));
   // forward: b -> a
@@ -218,7 +229,7 @@ static int run_stage2(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
   if (p.use_blk) { for (int c = N_BLK_CLASSES - 1; c >= 0; --c) if ((rc = launch_fwd2(p, c, nsm * 8, e->cls[c]))) return rc; }
   if ((rc = fan_in(e))) return rc;
   CKM_CUDA(cudaEventRecord(e->ev[5], st));
-  e->stats.kernel_launches += 3 + N_BLK_CLASSES + (p.use_blk ? N_BLK_CLASSES : 0);
+  e->stats.kernel_launches += 3 + (p.use_blk ? 2 * N_BLK_CLASSES : 0);
   s2.fwd_list = s2.a.as<Candidate>();
   return CKM_OK;
 }
@@ -358,20 +369,29 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
     n_pairs = (int64_t)db->nseq * nmodels;
   }
   std::memset(&e->stats, 0, sizeof(e->stats));
+  if (n_pairs > ((int64_t)1 << 40)) { set_error("ckm_search: more than 2^40 (ORF x HMM) pairs in one call; search fewer bins per call"); return CKM_ECAPACITY; }
   CKM_CUDA(cudaEventRecord(e->ev[8], st));
   Trace tr;
   Stage1 s1; Stage2 s2;
-  if ((rc = run_stage1(e, m, db, am, std::max<int64_t>(n_pairs, 1), s1, nullptr))) return rc;
-  if ((rc = run_stage2(e, m, db, am, s1, s2, nullptr, nullptr, nullptr, nullptr))) return rc;
   int32_t ctr[CTR_N];
   unsigned long long cells = 0;
-  CKM_CUDA(cudaMemcpyAsync(ctr, e->d_counters, sizeof(ctr), cudaMemcpyDeviceToHost, st));
-  CKM_CUDA(cudaMemcpyAsync(&cells, s1.cells.p, sizeof(cells), cudaMemcpyDeviceToHost, st));
-  CKM_CUDA(cudaStreamSynchronize(st));
-  tr.mark("filters done");
-  if (ctr[CTR_CAND] > s1.cand_cap || ctr[CTR_MSV] > s1.pass_cap || ctr[CTR_BIAS] > s2.cap || ctr[CTR_VIT] > s2.cap || ctr[CTR_FWD] > s2.cap) {
-    set_error("candidate queue overflow in the filter cascade"); return CKM_ECAPACITY;
+  for (int attempt = 0;; ++attempt) {
+    // a candidate-dense input (many pairs past SSV) overflows the default queues: the cascade is re-run with larger ones
+    if ((rc = run_stage1(e, m, db, am, std::max<int64_t>(n_pairs, 1), s1, nullptr, attempt))) return rc;
+    if ((rc = run_stage2(e, m, db, am, s1, s2, nullptr, nullptr, nullptr, nullptr))) return rc;
+    CKM_CUDA(cudaMemcpyAsync(ctr, e->d_counters, sizeof(ctr), cudaMemcpyDeviceToHost, st));
+    CKM_CUDA(cudaMemcpyAsync(&cells, s1.cells.p, sizeof(cells), cudaMemcpyDeviceToHost, st));
+    CKM_CUDA(cudaStreamSynchronize(st));
+    const bool over = ctr[CTR_CAND] > s1.cand_cap || ctr[CTR_MSV] > s1.pass_cap || ctr[CTR_BIAS] > s2.cap || ctr[CTR_VIT] > s2.cap || ctr[CTR_FWD] > s2.cap ||
+                      ctr[CTR_VREDO] > s2.cap;
+    if (!over) break;
+    if (attempt >= 2 || (s1.cand_cap >= std::min<int64_t>(n_pairs, QUEUE_MAX) && s1.pass_cap >= std::min<int64_t>(n_pairs, QUEUE_MAX))) {
+      set_error("candidate queue overflow in the filter cascade: more than 2^30 candidate pairs in one batch; search fewer bins per call");
+      return CKM_ECAPACITY;
+    }
+    e->stats.n_queue_retries++;
   }
+  tr.mark("filters done");
   e->stats.n_pairs = n_pairs; e->stats.n_cells = (int64_t)cells;
   e->stats.n_ssv_cand = ctr[CTR_CAND]; e->stats.n_past_msv = ctr[CTR_MSV]; e->stats.n_past_bias = ctr[CTR_BIAS];
   e->stats.n_past_vit = ctr[CTR_VIT]; e->stats.n_past_fwd = ctr[CTR_FWD]; e->stats.n_vit_redo = ctr[CTR_VREDO];
@@ -547,7 +567,7 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
         tr.mark("batch 1 + ensemble done");
         for (size_t mi = 0; mi < multi_idx.size(); ++mi) {
           int c = 0;
-          for (Envelope en : multi_envs[mi]) { if (c >= ENS_MAXENV) break; en.slot = reg_slot[multi_idx[mi]] + c++; envs2.push_back(en); }
+          for (Envelope en : multi_envs[mi]) { en.slot = reg_slot[multi_idx[mi]] + c++; envs2.push_back(en); }     // at most ENS_MAXENV (ensembles_collect refuses more)
         }
         if ((rc = run_env_batch(envs2, denvs2, deorder2, false))) return rc;
         tr.mark("envelope batch 2 done");
@@ -718,7 +738,7 @@ int ckm_viterbi_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_
     p.ms = m->d_scalars; p.bias_eo = m->d_bias_eo; p.rwv = m->d_rwv; p.twv = m->d_twv; p.rfv = m->d_rfv; p.tfv = m->d_tfv;
     p.twb = m->d_twb; p.rwb = m->d_rwb; p.tfb = m->d_tfb; p.rfb = m->d_rfb; p.twp = m->d_twp; p.rwp = m->d_rwp;
     p.row_elems = ((m->maxM + 31) / 32) * 32 + 64;
-    p.F1 = 0.02; p.F2 = 1e-3; p.F3 = 1e-5; p.use_blk = 1;
+    p.F1 = 0.02; p.F2 = 1e-3; p.F3 = 1e-5; p.use_blk = (mode == 2) ? 0 : 1;      // mode 2: every pair through the chunked shared-memory kernel
     p.dense_vit = dvit.as<float>(); p.model_slot = am.model_slot.as<int32_t>(); p.nseq = db->nseq;
     p.redo = dredo.as<Candidate>(); p.redo_count = e->d_counters + CTR_VREDO; p.redo_cap = (int32_t)nf;
     p.in = din.as<Candidate>(); p.in_count = e->d_counters + CTR_BIAS; p.in_cap = (int32_t)nf;
@@ -730,7 +750,7 @@ int ckm_viterbi_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_
       p.in = dredo.as<Candidate>(); p.in_count = e->d_counters + CTR_VREDO;
     }
     if ((rc = fan_out(e))) return rc;
-    for (int c = 0; c < N_BLK_CLASSES; ++c) if ((rc = launch_vit2(p, c, nsm * 8, e->cls[c]))) return rc;
+    if (p.use_blk) { for (int c = 0; c < N_BLK_CLASSES; ++c) if ((rc = launch_vit2(p, c, nsm * 8, e->cls[c]))) return rc; }
     if ((rc = launch_vit(p, nsm * 4, e->cls[N_BLK_CLASSES]))) return rc;
     if ((rc = fan_in(e))) return rc;
   }

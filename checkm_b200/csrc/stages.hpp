@@ -42,6 +42,7 @@ struct MsvParams {
   const int32_t *model_slot;   // database model index -> row of xj_dense
   int32_t nseq;
   int32_t row_bytes;           // shared-memory bytes of one DP row (>= maxM+2)
+  int32_t use_blk;             // 1: models with msv2_ok go to the lane-blocked kernels, 0: every candidate to msv_exact_kernel
   double F1;
 };
 

@@ -111,14 +111,14 @@ class Engine:
                                         out.ctypes.data))
         return out
 
-    def viterbi_scores(self, models, db, model_idx=None, int32_only=False):
+    def viterbi_scores(self, models, db, model_idx=None, int32_only=False, chunked_only=False):
         """Dense [nmodels, nseq] float32 ViterbiFilter scores of every pair (packed int16x2 kernel + int32 redo list, or the
         int32 kernels alone)."""
         nm = models.n if model_idx is None else len(model_idx)
         out = np.empty((nm, db.nseq), dtype=np.float32)
         mi = None if model_idx is None else np.ascontiguousarray(model_idx, dtype=np.int32)
         check(_lib.lib().ckm_viterbi_scores(self._h, models._h, None if mi is None else mi.ctypes.data, nm, db._h,
-                                            1 if int32_only else 0, out.ctypes.data))
+                                            2 if chunked_only else (1 if int32_only else 0), out.ctypes.data))
         return out
 
     def filter_scores(self, models, db, model_idx=None):

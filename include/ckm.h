@@ -81,6 +81,7 @@ typedef struct {
   float   ms_ssv, ms_msv, ms_bias, ms_vit, ms_fwd, ms_domdef, ms_total;   /* CUDA-event times of the last search */
   int64_t kernel_launches;
   int64_t n_vit_redo;     /* pairs the packed Viterbi kernel handed to the int32 kernel (strong hits, guard conditions) */
+  int64_t n_queue_retries;/* times the filter cascade was re-run with larger candidate queues (candidate-dense input) */
 } ckm_stats;
 
 /* ---- per-bin QA row = the integers/floats behind CheckM's table
@@ -154,7 +155,8 @@ int  ckm_filter_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_
                        uint8_t *passed_out /* bit0 msv, bit1 bias, bit2 vit, bit3 fwd; each nmodels*nseq */);
 
 /* ViterbiFilter score (nats) of EVERY pair, through the production kernels: the packed int16x2 kernel with its int32
- * redo list (mode 0) or the int32 kernels alone (mode 1).  +inf = int16 overflow, -inf = no path.  n_vit_redo of
+ * redo list (mode 0), the int32 kernels alone (mode 1), or the chunked shared-memory int32 kernel for every model, which
+ * production uses only beyond M = 1024 (mode 2).  +inf = int16 overflow, -inf = no path.  n_vit_redo of
  * ckm_last_stats says how many pairs took the redo route. */
 int  ckm_viterbi_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_idx, int32_t nmodels,
                         const ckm_seqdb *db, int32_t mode, float *vit_out /* nmodels*nseq */);

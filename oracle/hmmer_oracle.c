@@ -324,10 +324,13 @@ orc_profile *orc_profile_create(const orc_hmm *hmm)
   return p;
 }
 
+void orc_profile_enable_simd(orc_profile *p) { if (p && !p->striped) p->striped = orc_striped_create(p); }
+
 void orc_profile_free(orc_profile *p)
 {
   if (!p) return;
   free(p->tsc); free(p->bm); free(p->msc); free(p->rbv); free(p->rwv); free(p->twv); free(p->rfv); free(p->tfv);
+  orc_striped_free(p->striped);
   free(p);
 }
 
@@ -574,7 +577,7 @@ static specials make_specials(int Lcfg, int multihit)
   return s;
 }
 
-static int forward_engine(const orc_profile *p, const uint8_t *dsq, int L, specials sp, fmx *ox, float *ret_sc)
+static int forward_engine_seq(const orc_profile *p, const uint8_t *dsq, int L, specials sp, fmx *ox, float *ret_sc)
 {
   int M = p->M;
   float *dpc = fmx_row(ox, 0), *dpp;
@@ -612,19 +615,19 @@ static int forward_engine(const orc_profile *p, const uint8_t *dsq, int L, speci
       float inv = 1.0f / xE;
       for (int k = 1; k <= M; k++) { dpc[k * 3 + C_M] *= inv; dpc[k * 3 + C_D] *= inv; dpc[k * 3 + C_I] *= inv; }
       ox->xmx[i * X_NX + X_SCALE] = xE;
-      ox->totscale += (float)log(xE);
+      ox->totscale += (float)log((double)xE);
       xE = 1.0f;
     } else ox->xmx[i * X_NX + X_SCALE] = 1.0f;
     float *xr = ox->xmx + i * X_NX;
     xr[X_E] = xE; xr[X_N] = xN; xr[X_J] = xJ; xr[X_B] = xB; xr[X_C] = xC;
   }
   if (isnan(xC) || (L > 0 && xC == 0.0f) || isinf(xC)) { if (ret_sc) *ret_sc = -INFINITY; return 1; }
-  if (ret_sc) *ret_sc = ox->totscale + (float)log(xC * sp.nmove);
+  if (ret_sc) *ret_sc = ox->totscale + (float)log((double)(xC * sp.nmove));
   return 0;
 }
 
 /* Backward, scaled with the Forward matrix's per-row scale factors. */
-static int backward_engine(const orc_profile *p, const uint8_t *dsq, int L, specials sp, const fmx *fwd, fmx *bck, float *ret_sc)
+static int backward_engine_seq(const orc_profile *p, const uint8_t *dsq, int L, specials sp, const fmx *fwd, fmx *bck, float *ret_sc)
 {
   int M = p->M;
   float *dpc = NULL, *dpp = NULL;
@@ -679,6 +682,244 @@ static int backward_engine(const orc_profile *p, const uint8_t *dsq, int L, spec
   return 0;
 }
 
+
+/* =====================================================================================
+ * Evaluation order of the fp32 sums.
+ *
+ * fp32 addition is not associative, so the last bits of a Forward score depend on the order in which the cells of a row
+ * are added up -- HMMER's own results differ between its SSE, VMX, NEON and generic builds for exactly this reason.
+ * Two orders are restated here:
+ *   ORC_ORDER_SEQUENTIAL  the textbook order: k = 1..M left to right (HMMER's generic implementation).
+ *   ORC_ORDER_CANONICAL   the order the engine under test is specified to use (DESIGN.md "canonical order"): the model is cut
+ *                         into 32 blocks of Q consecutive positions (Q = orc_block_width(M)); a row sum is the sum of the 32
+ *                         block sums taken in a butterfly (pairs 16 apart, then 8, 4, 2, 1); the delete chain
+ *                         D(k+1) = M(k) tMD(k) + D(k) tDD(k) is carried across blocks by composing the 32 affine block maps in
+ *                         a doubling scan and then replayed inside each block.  Models longer than 1024 positions have no
+ *                         blocked form; for them this order IS the sequential one.
+ * Same recurrences, same per-cell arithmetic; only the association of the sums differs (tests bound the difference
+ * between the two orders below 1e-3 bits, typically 1e-5).  With the canonical order the GPU's floats are reproduced bit for
+ * bit, which is what lets the parity tests compare printed domtblout text.
+ * ===================================================================================== */
+static int g_order = ORC_ORDER_CANONICAL;
+void orc_set_order(int order) { g_order = order; }
+int  orc_get_order(void) { return g_order; }
+int  orc_block_width(int M)
+{
+  return (M <= 64) ? 2 : (M <= 128) ? 4 : (M <= 192) ? 6 : (M <= 256) ? 8 : (M <= 384) ? 12 : (M <= 512) ? 16 : (M <= 640) ? 20 :
+         (M <= 768) ? 24 : (M <= 896) ? 28 : (M <= 1024) ? 32 : 0;
+}
+#define NB 32            /* blocks */
+#define QMAX 32
+
+/* butterfly sum of 32 block values: every block ends up with the same total */
+static float butterfly_sum(const float *v)
+{
+  float a[NB], b[NB];
+  memcpy(a, v, sizeof(a));
+  for (int o = 16; o > 0; o >>= 1) {
+    for (int l = 0; l < NB; l++) b[l] = a[l] + a[l ^ o];
+    memcpy(a, b, sizeof(a));
+  }
+  return a[0];
+}
+
+static int forward_engine_blk(const orc_profile *p, const uint8_t *dsq, int L, specials sp, fmx *ox, float *ret_sc, int Q)
+{
+  const int M = p->M;
+  static const float zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float (*Mx)[QMAX] = (float (*)[QMAX])calloc(NB * 3, sizeof(float[QMAX]));
+  float (*Ix)[QMAX] = Mx + NB, (*Dx)[QMAX] = Ix + NB;
+  float md[NB][QMAX], esum[NB], Bs[NB], Ts[NB], Bn[NB], Tn[NB];
+  float *dpc = fmx_row(ox, 0);
+  for (int k = 0; k <= M; k++) dpc[k * 3 + C_M] = dpc[k * 3 + C_D] = dpc[k * 3 + C_I] = 0.0f;
+  float xE = 0.0f, xN = 1.0f, xJ = 0.0f, xB = sp.nmove, xC = 0.0f;
+  ox->xmx[X_E] = xE; ox->xmx[X_N] = xN; ox->xmx[X_J] = xJ; ox->xmx[X_B] = xB; ox->xmx[X_C] = xC; ox->xmx[X_SCALE] = 1.0f;
+  ox->totscale = 0.0f;
+  for (int i = 1; i <= L; i++) {
+    const float *rp = p->rfv + (size_t)dsq[i - 1] * (M + 1);
+    float pm_in[NB], pi_in[NB], pd_in[NB];
+    for (int l = 0; l < NB; l++) {
+      pm_in[l] = l ? Mx[l - 1][Q - 1] : 0.0f; pi_in[l] = l ? Ix[l - 1][Q - 1] : 0.0f; pd_in[l] = l ? Dx[l - 1][Q - 1] : 0.0f;
+    }
+    for (int l = 0; l < NB; l++) {
+      float es = 0.0f;
+      for (int q = Q - 1; q >= 0; q--) {
+        const int k = l * Q + q + 1;
+        const float *tf = (k <= M) ? p->tfv + k * 8 : zero8;
+        const float e = (k <= M) ? rp[k] : 0.0f;
+        const float pm = (q > 0) ? Mx[l][q - 1] : pm_in[l], pi = (q > 0) ? Ix[l][q - 1] : pi_in[l], pd = (q > 0) ? Dx[l][q - 1] : pd_in[l];
+        float sv = xB * tf[T_BM];
+        sv += pm * tf[T_MM];
+        sv += pi * tf[T_IM];
+        sv += pd * tf[T_DM];
+        sv *= e;
+        const float nI = Mx[l][q] * tf[T_MI] + Ix[l][q] * tf[T_II];
+        md[l][q] = sv * tf[T_MD];
+        Mx[l][q] = sv; Ix[l][q] = nI;
+        es += sv;
+      }
+      esum[l] = es;
+      float Bb = 0.0f, Tb = 1.0f;
+      for (int q = 0; q < Q; q++) {
+        const int k = l * Q + q + 1;
+        const float tdd = (k <= M) ? p->tfv[k * 8 + T_DD] : 0.0f;
+        Bb = md[l][q] + Bb * tdd; Tb *= tdd;
+      }
+      Bs[l] = Bb; Ts[l] = Tb;
+    }
+    for (int o = 1; o < NB; o <<= 1) {
+      for (int l = 0; l < NB; l++) {
+        if (l >= o) { Bn[l] = Bs[l] + Bs[l - o] * Ts[l]; Tn[l] = Ts[l] * Ts[l - o]; }
+        else { Bn[l] = Bs[l]; Tn[l] = Ts[l]; }
+      }
+      memcpy(Bs, Bn, sizeof(Bs)); memcpy(Ts, Tn, sizeof(Ts));
+    }
+    for (int l = 0; l < NB; l++) {
+      float d = l ? Bs[l - 1] : 0.0f;
+      for (int q = 0; q < Q; q++) {
+        const int k = l * Q + q + 1;
+        const float tdd = (k <= M) ? p->tfv[k * 8 + T_DD] : 0.0f;
+        Dx[l][q] = (k <= M) ? d : 0.0f;
+        esum[l] += Dx[l][q];
+        d = md[l][q] + d * tdd;
+      }
+    }
+    xE = butterfly_sum(esum);
+    xN = xN * sp.nloop;
+    xC = (xC * sp.nloop) + (xE * sp.emove);
+    xJ = (xJ * sp.nloop) + (xE * sp.eloop);
+    xB = (xJ * sp.nmove) + (xN * sp.nmove);
+    float scale = 1.0f;
+    if (xE > 1.0e4f) {
+      scale = xE;
+      const float inv = 1.0f / xE;
+      xN = xN / xE; xC = xC / xE; xJ = xJ / xE; xB = xB / xE;
+      for (int l = 0; l < NB; l++) for (int q = 0; q < Q; q++) { Mx[l][q] *= inv; Dx[l][q] *= inv; Ix[l][q] *= inv; }
+      ox->totscale += (float)log((double)xE);
+      xE = 1.0f;
+    }
+    if (ox->full) {
+      dpc = fmx_row(ox, i);
+      dpc[C_M] = dpc[C_D] = dpc[C_I] = 0.0f;
+      for (int k = 1; k <= M; k++) { const int l = (k - 1) / Q, q = (k - 1) % Q; dpc[k * 3 + C_M] = Mx[l][q]; dpc[k * 3 + C_D] = Dx[l][q]; dpc[k * 3 + C_I] = Ix[l][q]; }
+    }
+    float *xr = ox->xmx + i * X_NX;
+    xr[X_E] = xE; xr[X_N] = xN; xr[X_J] = xJ; xr[X_B] = xB; xr[X_C] = xC; xr[X_SCALE] = scale;
+  }
+  free(Mx);
+  if (isnan(xC) || (L > 0 && xC == 0.0f) || isinf(xC)) { if (ret_sc) *ret_sc = -INFINITY; return 1; }
+  if (ret_sc) *ret_sc = ox->totscale + (float)log((double)(xC * sp.nmove));
+  return 0;
+}
+
+static int backward_engine_blk(const orc_profile *p, const uint8_t *dsq, int L, specials sp, const fmx *fwd, fmx *bck, float *ret_sc, int Q)
+{
+  const int M = p->M;
+  static const float zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float (*Mx)[QMAX] = (float (*)[QMAX])calloc(NB * 3, sizeof(float[QMAX]));
+  float (*Ix)[QMAX] = Mx + NB, (*Dx)[QMAX] = Ix + NB;
+  float em[NB][QMAX], cb[NB][QMAX], part[NB], Bs[NB], Ts[NB], Bn[NB], Tn[NB];
+  float xC = 0.0f, xE = 0.0f, xJ = 0.0f, xN = 0.0f, xB = 0.0f;
+  bck->totscale = 0.0f;
+  for (int i = L; i >= 0; i--) {
+    const float *rp = (i < L) ? p->rfv + (size_t)dsq[i] * (M + 1) : NULL;
+    if (i == L) {
+      xC = sp.nmove; xE = xC * sp.emove; xB = 0.0f; xJ = 0.0f; xN = 0.0f;
+      for (int l = 0; l < NB; l++) for (int q = 0; q < Q; q++) em[l][q] = 0.0f;
+    } else {
+      for (int l = 0; l < NB; l++) {
+        float pt = 0.0f;
+        for (int q = 0; q < Q; q++) {
+          const int k = l * Q + q + 1;
+          const float e = (k <= M) ? rp[k] : 0.0f, tbm = (k <= M) ? p->tfv[k * 8 + T_BM] : 0.0f;
+          em[l][q] = Mx[l][q] * e; pt += em[l][q] * tbm;
+        }
+        part[l] = pt;
+      }
+      xB = butterfly_sum(part);
+      xC = xC * sp.nloop;
+      xJ = (xB * sp.nmove) + (xJ * sp.nloop);
+      xN = (xB * sp.nmove) + (xN * sp.nloop);
+      xE = (xC * sp.emove) + (xJ * sp.eloop);
+    }
+    const float s = (i >= 1) ? fwd->xmx[i * X_NX + X_SCALE] : 1.0f;
+    float *dpc = fmx_row(bck, i);
+    if (i >= 1) {
+      const float inv = (s > 1.0f) ? 1.0f / s : 1.0f;
+      for (int l = 0; l < NB; l++) {
+        const float em_next = (l < NB - 1) ? em[l + 1][0] : 0.0f;
+        const int kn = (l + 1) * Q + 1;                        /* first position of the next block */
+        const float *tn = (l < NB - 1 && kn <= M) ? p->tfv + kn * 8 : zero8;
+        float Bb = 0.0f, Tb = 1.0f;
+        for (int q = Q - 1; q >= 0; q--) {
+          const int k = l * Q + q + 1;
+          const float mnext = (q < Q - 1) ? em[l][q + 1] : em_next;
+          const float *t0n = (q < Q - 1) ? ((k + 1 <= M) ? p->tfv + (k + 1) * 8 : zero8) : tn;
+          const float tdm = t0n[T_DM];
+          const int in = (k <= M);
+          cb[l][q] = in ? (xE + ((k < M) ? mnext * tdm : 0.0f)) : 0.0f;
+          const float tdd = in ? p->tfv[k * 8 + T_DD] : 0.0f;
+          Bb = cb[l][q] + Bb * tdd; Tb *= tdd;
+        }
+        Bs[l] = Bb; Ts[l] = Tb;
+      }
+      for (int o = 1; o < NB; o <<= 1) {
+        for (int l = 0; l < NB; l++) {
+          if (l + o < NB) { Bn[l] = Bs[l] + Bs[l + o] * Ts[l]; Tn[l] = Ts[l] * Ts[l + o]; }
+          else { Bn[l] = Bs[l]; Tn[l] = Ts[l]; }
+        }
+        memcpy(Bs, Bn, sizeof(Bs)); memcpy(Ts, Tn, sizeof(Ts));
+      }
+      float nM[QMAX], nI[QMAX], nD[QMAX];
+      for (int l = 0; l < NB; l++) {
+        const float em_next = (l < NB - 1) ? em[l + 1][0] : 0.0f;
+        const int kn = (l + 1) * Q + 1;
+        const float *tn = (l < NB - 1 && kn <= M) ? p->tfv + kn * 8 : zero8;
+        float dnext = (l < NB - 1) ? Bs[l + 1] : 0.0f;
+        for (int q = Q - 1; q >= 0; q--) {
+          const int k = l * Q + q + 1;
+          const int in = (k <= M);
+          const float *t1 = in ? p->tfv + k * 8 : zero8;
+          const float mnext = (q < Q - 1) ? em[l][q + 1] : em_next;
+          const float *t0n = (q < Q - 1) ? ((k + 1 <= M) ? p->tfv + (k + 1) * 8 : zero8) : tn;
+          const float tmm = (k < M) ? t0n[T_MM] : 0.0f, tim = (k < M) ? t0n[T_IM] : 0.0f;
+          const float inext = (i < L) ? Ix[l][q] : 0.0f;
+          const float dv = in ? (cb[l][q] + dnext * t1[T_DD]) : 0.0f;
+          float mv = xE + mnext * tmm + inext * t1[T_MI] + dnext * t1[T_MD];
+          float iv = mnext * tim + inext * t1[T_II];
+          if (!in) { mv = 0.0f; iv = 0.0f; }
+          nM[q] = mv * inv; nI[q] = iv * inv; nD[q] = dv * inv;
+          dnext = dv;
+        }
+        for (int q = 0; q < Q; q++) { Mx[l][q] = nM[q]; Ix[l][q] = nI[q]; Dx[l][q] = nD[q]; }
+      }
+      if (s > 1.0f) { xE = xE / s; xN = xN / s; xJ = xJ / s; xB = xB / s; xC = xC / s; }
+    } else {
+      xC = 0.0f; xJ = 0.0f; xE = 0.0f;
+      for (int l = 0; l < NB; l++) for (int q = 0; q < Q; q++) { Mx[l][q] = 0.0f; Ix[l][q] = 0.0f; Dx[l][q] = 0.0f; }
+    }
+    dpc[C_M] = dpc[C_D] = dpc[C_I] = 0.0f;
+    for (int k = 1; k <= M; k++) { const int l = (k - 1) / Q, q = (k - 1) % Q; dpc[k * 3 + C_M] = Mx[l][q]; dpc[k * 3 + C_D] = Dx[l][q]; dpc[k * 3 + C_I] = Ix[l][q]; }
+    bck->totscale += (float)log((double)s);
+    float *xr = bck->xmx + i * X_NX;
+    xr[X_E] = xE; xr[X_N] = xN; xr[X_J] = xJ; xr[X_B] = xB; xr[X_C] = xC; xr[X_SCALE] = s;
+  }
+  free(Mx);
+  if (ret_sc) *ret_sc = bck->totscale + (float)log((double)xN);
+  return 0;
+}
+
+static int forward_engine(const orc_profile *p, const uint8_t *dsq, int L, specials sp, fmx *ox, float *ret_sc)
+{
+  const int Q = (g_order == ORC_ORDER_CANONICAL) ? orc_block_width(p->M) : 0;
+  return Q ? forward_engine_blk(p, dsq, L, sp, ox, ret_sc, Q) : forward_engine_seq(p, dsq, L, sp, ox, ret_sc);
+}
+static int backward_engine(const orc_profile *p, const uint8_t *dsq, int L, specials sp, const fmx *fwd, fmx *bck, float *ret_sc)
+{
+  const int Q = (g_order == ORC_ORDER_CANONICAL) ? orc_block_width(p->M) : 0;
+  return Q ? backward_engine_blk(p, dsq, L, sp, fwd, bck, ret_sc, Q) : backward_engine_seq(p, dsq, L, sp, fwd, bck, ret_sc);
+}
+
 int orc_forward_parser(const orc_profile *p, const uint8_t *dsq, int L, float *ret_sc)
 {
   fmx *f = fmx_create(p->M, L, 0);
@@ -706,7 +947,8 @@ int orc_filters(const orc_profile *p, const uint8_t *dsq, int L, orc_filter_resu
   r->vit_sc = NAN; r->fwd_sc = NAN; r->filtersc = NAN;
   if (L == 0) return 0;
   r->nullsc = orc_null1(L);
-  orc_msv(p, dsq, L, &r->msv_sc, &r->msv_xJ);
+  if (p->striped) orc_msv_simd(p, p->striped, dsq, L, &r->msv_sc, &r->msv_xJ);
+  else            orc_msv(p, dsq, L, &r->msv_sc, &r->msv_xJ);
   float seq_score = (r->msv_sc - r->nullsc) / (float)LOG2C;
   double P = gumbel_surv(seq_score, ev[ORC_MMU], ev[ORC_MLAMBDA]);
   if (P > F1_DEFAULT) return 0;
@@ -717,7 +959,8 @@ int orc_filters(const orc_profile *p, const uint8_t *dsq, int L, orc_filter_resu
   if (P > F1_DEFAULT) return 0;
   r->passed_bias = 1;
   if (P > F2_DEFAULT) {
-    orc_vitfilter(p, dsq, L, &r->vit_sc);
+    if (p->striped) orc_vitfilter_simd(p, p->striped, dsq, L, &r->vit_sc);
+    else            orc_vitfilter(p, dsq, L, &r->vit_sc);
     seq_score = (r->vit_sc - r->filtersc) / (float)LOG2C;
     P = gumbel_surv(seq_score, ev[ORC_VMU], ev[ORC_VLAMBDA]);
     if (P > F2_DEFAULT) return 0;
@@ -819,10 +1062,21 @@ static void null2_by_expectation(const orc_profile *p, const fmx *pp, float *nul
   for (int k = 1; k <= M; k++) { em[k] *= norm; ei[k] *= norm; }
   xn *= norm; xc *= norm; xj *= norm;
   float xfactor = xn + xc + xj;
+  const int Q = (g_order == ORC_ORDER_CANONICAL) ? orc_block_width(M) : 0;
   for (int x = 0; x < ORC_K; x++) {
     const float *rp = p->rfv + (size_t)x * (M + 1);
     float sv = 0.0f;
-    for (int k = 1; k <= M; k++) { sv += em[k] * rp[k]; sv += ei[k]; }
+    if (Q) {                                             /* 32 block sums, then the butterfly */
+      float part[NB];
+      for (int l = 0; l < NB; l++) {
+        float pt = 0.0f;
+        for (int q = 0; q < Q; q++) { const int k = l * Q + q + 1; if (k <= M) { pt += em[k] * rp[k]; pt += ei[k]; } else { pt += 0.0f; pt += 0.0f; } }
+        part[l] = pt;
+      }
+      sv = butterfly_sum(part);
+    } else {
+      for (int k = 1; k <= M; k++) { sv += em[k] * rp[k]; sv += ei[k]; }
+    }
     null2[x] = sv + xfactor;
   }
   for (int x = ORC_K + 1; x <= ORC_KP - 3; x++) {      /* degenerate: plain average of the odds */
@@ -1198,7 +1452,13 @@ static void null2_by_trace(const orc_profile *p, const trace_t *tr, int z1, int 
   for (int x = 0; x < ORC_K; x++) {
     const float *rp = p->rfv + (size_t)x * (M + 1);
     float sv = 0.0f;
-    for (int k = 1; k <= M; k++) { sv += cm[k] * rp[k]; sv += ci[k]; }
+    if (g_order == ORC_ORDER_CANONICAL) {                /* 32 interleaved partial sums (k = l+1, l+33, ...), then the butterfly */
+      float part[NB];
+      for (int l = 0; l < NB; l++) { float pt = 0.0f; for (int k = l + 1; k <= M; k += NB) { pt += cm[k] * rp[k]; pt += ci[k]; } part[l] = pt; }
+      sv = butterfly_sum(part);
+    } else {
+      for (int k = 1; k <= M; k++) { sv += cm[k] * rp[k]; sv += ci[k]; }
+    }
     null2[x] = sv + xfactor;
   }
   for (int x = ORC_K + 1; x <= ORC_KP - 3; x++) {
@@ -1226,7 +1486,7 @@ static int rescore_isolated_domain(ddef_t *dd, const orc_profile *p, const uint8
   /* null2 needs the posteriors; the OA fill then reuses ox1 */
   if (!null2_is_done) {
     null2_by_expectation(p, ox2, null2);
-    for (int pos = i; pos <= j; pos++) dd->n2sc[pos] = logf(null2[dsq[pos - 1]]);
+    for (int pos = i; pos <= j; pos++) dd->n2sc[pos] = (float)log((double)null2[dsq[pos - 1]]);
   }
   oasc = optimal_accuracy(p, sp, ox2, ox1);
   int hf, ht, sf, st;
@@ -1248,7 +1508,7 @@ static void region_trace_ensemble(ddef_t *dd, const orc_profile *p, const uint8_
   int Lr = jreg - ireg + 1, M = p->M;
   specials sp = make_specials(Lseq, 1);
   fmx *fwd = fmx_create(M, Lr, 1);
-  forward_engine(p, dsq + ireg - 1, Lr, sp, fwd, NULL);
+  forward_engine_seq(p, dsq + ireg - 1, Lr, sp, fwd, NULL);      /* the sampled matrix is evaluated left to right in both orders */
   lcg_t rng; lcg_init(&rng, 42);
   trace_t tr; memset(&tr, 0, sizeof(tr));
   float *cnt = (float *)malloc(sizeof(float) * 2 * (M + 1));
@@ -1273,7 +1533,7 @@ static void region_trace_ensemble(ddef_t *dd, const orc_profile *p, const uint8_
     }
     for (; pos <= Lr; pos++) dd->n2sc[ireg + pos - 1] += 1.0f;
   }
-  for (int pos = ireg; pos <= jreg; pos++) dd->n2sc[pos] = logf(dd->n2sc[pos] / (float)NSAMPLES);
+  for (int pos = ireg; pos <= jreg; pos++) dd->n2sc[pos] = (float)log((double)(dd->n2sc[pos] / (float)NSAMPLES));
   *ret_sig = sp_cluster(sps, nsp, NSAMPLES, ret_nc);
   free(sps); free(cnt); free(tr.st); free(tr.k); free(tr.i);
   fmx_free(fwd);

@@ -61,6 +61,7 @@ typedef struct {
   /* Forward/Backward (odds ratios) */
   float   *rfv;        /* ORC_KP*(M+1)                                                */
   float   *tfv;        /* (M+1)*8 same order as twv                                   */
+  void    *striped;    /* SSE2 striped copies (simd_filters.c), NULL until orc_profile_enable_simd() */
 } orc_profile;
 
 /* one reported (or unreported) domain of a hit */
@@ -107,6 +108,21 @@ orc_hmm *orc_hmm_at(orc_hmm *hmms, int i);
 /* ---- profile ---- */
 orc_profile *orc_profile_create(const orc_hmm *hmm);
 void         orc_profile_free(orc_profile *p);
+
+/* ---- SSE2 striped MSV / Viterbi filters for the CPU baseline of bench.py (simd_filters.c): same scores as the scalar
+ * functions below; once enabled on a profile, orc_filters / orc_pipeline / orc_search use them ---- */
+void  orc_profile_enable_simd(orc_profile *p);
+void *orc_striped_create(const orc_profile *p);
+void  orc_striped_free(void *h);
+int   orc_msv_simd(const orc_profile *p, const void *h, const uint8_t *dsq, int L, float *ret_sc, int *ret_xJ);
+int   orc_vitfilter_simd(const orc_profile *p, const void *h, const uint8_t *dsq, int L, float *ret_sc);
+
+/* ---- evaluation order of the fp32 row sums (see hmmer_oracle.c): sequential (textbook) or canonical (the engine's
+ * specified blocked order, the default) ---- */
+enum { ORC_ORDER_SEQUENTIAL = 0, ORC_ORDER_CANONICAL = 1 };
+void orc_set_order(int order);
+int  orc_get_order(void);
+int  orc_block_width(int M);
 
 /* ---- individual stages (dsq is 0-based, length L) ---- */
 float orc_null1(int L);

@@ -72,6 +72,12 @@ def lib():
         L.orc_write_domtblout.argtypes = [C.POINTER(Results), C.POINTER(C.c_void_p), C.POINTER(C.c_char_p),
                                           C.POINTER(C.c_char_p), C.c_char_p]
         L.orc_digitize.argtypes = [C.c_char_p, C.c_int, C.c_void_p]
+        L.orc_profile_enable_simd.argtypes = [C.c_void_p]
+        L.orc_msv_simd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        L.orc_vitfilter_simd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float)]
+        L.orc_striped_create.restype = C.c_void_p
+        L.orc_striped_create.argtypes = [C.c_void_p]
+        L.orc_striped_free.argtypes = [C.c_void_p]
         L.orc_stage_scores.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int]
         _LIB = L
@@ -120,6 +126,11 @@ class HmmFile:
         self.headers = [C.cast(p, C.POINTER(HmmHeader)).contents for p in self.hmm_ptrs]
         self.prof_ptrs = [L.orc_profile_create(p) for p in self.hmm_ptrs]
         self.profiles = [C.cast(p, C.POINTER(Profile)).contents for p in self.prof_ptrs]
+
+    def enable_simd(self):
+        """Switch the MSV / Viterbi filters of every profile to the SSE2 striped versions (CPU baseline of bench.py)."""
+        for p in self.prof_ptrs:
+            lib().orc_profile_enable_simd(p)
 
     def names(self):
         return [h.name.decode() for h in self.headers]

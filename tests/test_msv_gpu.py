@@ -63,8 +63,14 @@ def test_msv_edge_lengths(engine, cpr_models, cpr_oracle, oracle):
     _check(engine, cpr_models, cpr_oracle, b, oracle)
 
 
-def test_msv_long_models_and_subset(engine, oracle, tmp_path):
-    """Tile classes J=4/8/16 and chained tiles (M >= 1024); a query subset."""
+@pytest.mark.parametrize('policy', [None, 'auto', '8'])
+def test_msv_long_models_and_subset(engine, oracle, tmp_path, policy, monkeypatch):
+    """Chained tiles (M >= 64 J) and a query subset, under every tile-width policy: the default J = 32 tiles, CKM_SSV_J=auto
+    (J = 4 / 8 / 16 by model length) and one fixed narrow width (the policy is read when the database is loaded)."""
+    if policy is None:
+        monkeypatch.delenv('CKM_SSV_J', raising=False)
+    else:
+        monkeypatch.setenv('CKM_SSV_J', policy)
     p = str(tmp_path / 'long.hmm')
     ms = synth.make_model_db(p, CPR_HMM, [30, 57, 130, 255, 256, 300, 511, 512, 700, 1023, 1024, 1100, 2500], seed=3)
     ohf = oracle.HmmFile(p)
@@ -73,3 +79,13 @@ def test_msv_long_models_and_subset(engine, oracle, tmp_path):
     _check(engine, models, ohf, b, oracle)
     _check(engine, models, ohf, b, oracle, model_idx=[12, 3, 10])
     models.close()
+
+
+def test_msv_chunked_kernel_on_short_models(engine, cpr_models, cpr_oracle, oracle, monkeypatch):
+    """CKM_BLK=0 sends every SSV candidate to msv_exact_kernel (shared-memory rows), which production uses only for models
+    without a lane-block class: same bytes, same pass set."""
+    monkeypatch.setenv('CKM_BLK', '0')
+    hm = synth.read_hmms(CPR_HMM)
+    b = synth.make_bin('b0', hm, seed=12, n_orfs=150, tandem_prob=0.1, max_len=1200)
+    n_pass, n_cand, _ = _check(engine, cpr_models, cpr_oracle, b, oracle)
+    assert n_pass > 20

@@ -192,3 +192,56 @@ def test_planted_homologs_are_found(cpr_oracle, oracle):
     found = set((r['model'], r['seqidx']) for r in rows)
     hit = sum((m, o) in found for m, o, _ in b.planted)
     assert hit >= 0.9 * len(b.planted), (hit, len(b.planted))      # a sampled homolog can legitimately fall below E = 0.1
+
+
+def test_evaluation_orders_agree(cpr_oracle, oracle):
+    """The oracle restates the fp32 row sums in two association orders (hmmer_oracle.c): sequential (textbook, HMMER's generic
+    build) and canonical (the engine's blocked order).  Same hit table; scores differ only by fp32 association noise -- the
+    same kind of difference that separates HMMER's SSE / VMX / NEON builds -- below the north-star tolerance of 1e-3 bits
+    except where a long bias sum amplifies it."""
+    hm = synth.read_hmms(CPR_HMM)
+    out = {}
+    try:
+        for order in (0, 1):
+            oracle.lib().orc_set_order(order)
+            rows = []
+            for seed, kw in ((32, dict(n_orfs=200, tandem_prob=0.5, max_len=1500)), (31, dict(n_orfs=300, max_len=1200))):
+                b = synth.make_bin('o', hm, seed=seed, **kw)
+                rp = oracle.search(cpr_oracle, b.residues, b.offsets, nthreads=os.cpu_count() or 4)
+                rows += oracle.hits_table(rp)
+                oracle.free_results(rp)
+            out[order] = rows
+    finally:
+        oracle.lib().orc_set_order(1)
+    key = lambda r: (r['model'], r['seqidx'], r['dom'], r['hmm_from'], r['hmm_to'], r['ali_from'], r['ali_to'], r['env_from'], r['env_to'])
+    assert [key(r) for r in out[0]] == [key(r) for r in out[1]] and len(out[0]) > 80
+    d = np.array([abs(a[k] - b[k]) for a, b in zip(out[0], out[1]) for k in ('full_score', 'dom_score')])
+    nb = np.array([abs(a['full_bias']) for a in out[0] for _ in range(2)])
+    print('sequential vs canonical order: median %.2g, 99%% %.2g, max %.2g bits' % (np.median(d), np.quantile(d, 0.99), d.max()))
+    assert np.median(d) < 1e-4 and (d <= 1e-3 + 1e-4 * nb).all()
+
+
+def test_simd_filters_equal_scalar(cpr_oracle, oracle):
+    """The SSE2 striped MSV / Viterbi filters of the CPU baseline (oracle/simd_filters.c) return the scalar functions' scores."""
+    hf = cpr_oracle
+    hm = synth.read_hmms(CPR_HMM)
+    L = oracle.lib()
+    rng = np.random.default_rng(5)
+    n = 0
+    for m in range(0, hf.n, 2):
+        h = L.orc_striped_create(hf.prof_ptrs[m])
+        seqs = [rng.choice(20, size=int(l), p=synth.BG).astype(np.uint8) for l in synth.random_lengths(rng, 25, hi=1500)]
+        seqs += [np.concatenate([rng.choice(20, size=30, p=synth.BG).astype(np.uint8), synth.emit_homolog(hm[m], rng)]) for _ in range(4)]
+        seqs += [synth.emit_homolog(hm[m], rng, k_from=hm[m].M // 3, k_to=2 * hm[m].M // 3) for _ in range(4)]
+        seqs += [np.concatenate([synth.emit_homolog(hm[m], rng), synth.emit_homolog(hm[m], rng)]), np.zeros(1, np.uint8), np.full(30, 27, np.uint8)]
+        for d in seqs:
+            sc1, xj1 = oracle.msv(hf, m, d)
+            sc, xj, v = C.c_float(), C.c_int(), C.c_float()
+            L.orc_msv_simd(hf.prof_ptrs[m], h, d.ctypes.data, len(d), C.byref(sc), C.byref(xj))
+            L.orc_vitfilter_simd(hf.prof_ptrs[m], h, d.ctypes.data, len(d), C.byref(v))
+            v1 = oracle.vitfilter(hf, m, d)
+            assert xj.value == xj1 and (sc.value == sc1 or (np.isinf(sc.value) and np.isinf(sc1))), (m, len(d))
+            assert v.value == v1 or (np.isinf(v.value) and np.isinf(v1) and np.sign(v.value) == np.sign(v1)), (m, len(d), v.value, v1)
+            n += 1
+        L.orc_striped_free(h)
+    assert n > 700

@@ -2,8 +2,9 @@
 strings and resultsParser.py:356-367 compares them with the GA/TC/NC cutoffs), so the GPU's printed rows must equal the
 oracle's printed rows -- not merely agree within a float tolerance.  Every bin below is searched on the device
 (ckm_search -> ckm_write_domtblout) and by the oracle (orc_search -> orc_write_domtblout); the data lines are compared
-field by field as text, and the float columns additionally at the north-star tolerance of 1e-3 bits, flat.
-The mismatch count is printed; the bar is 0."""
+field by field as text, and the float columns additionally bit for bit: for models with a blocked class (M <= 1024, all of
+CheckM's markers) the oracle evaluates the fp32 row sums in the engine's canonical order (oracle/hmmer_oracle.c), so there
+is no tolerance to state.  The mismatch count is printed; the bar is 0."""
 import os
 
 import numpy as np
@@ -13,7 +14,7 @@ from conftest import CPR_HMM
 from tools import synth
 
 pytestmark = pytest.mark.gpu
-TOL_BITS = 1e-3
+TOL_BITS = 0.0
 
 
 def _data_lines(path):
@@ -44,11 +45,11 @@ def _compare(glines, olines, hits, rows, tag, stats):
     worst = 0.0
     for r, h in zip(rows, hits):
         for a, b in ((r['full_score'], h['full_score']), (r['dom_score'], h['dom_score']), (r['full_bias'], h['full_bias']), (r['dom_bias'], h['dom_bias'])):
-            d = abs(float(a) - float(b))
+            d = abs(float(np.float32(a)) - float(b))
             worst = max(worst, d)
             stats.append(d)
             assert d <= TOL_BITS, (tag, r, h)
-        assert abs(float(r['acc']) - float(h['acc'])) <= 1e-4
+        assert abs(float(np.float32(r['acc'])) - float(h['acc'])) <= 1e-6
     print('%s: %d rows, %d differ as text, worst score/bias difference %.3g bits' % (tag, len(glines), len(bad), worst))
     return bad
 
@@ -84,5 +85,5 @@ def test_domtblout_text_identical_full_bin(engine, cpr_models, cpr_oracle, oracl
     g, o, hits, rows = _both_tables(engine, cpr_models, cpr_oracle, oracle, b, tmp_path, 'full')
     stats = []
     bad = _compare(g, o, hits, rows, 'full 1,900-ORF bin', stats)
-    assert len(g) >= 40
+    assert len(g) >= 30
     assert not bad, bad[:3]

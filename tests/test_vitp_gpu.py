@@ -69,6 +69,23 @@ def _compare(engine, models, ohf, oracle, res, off, model_idx=None, oracle_pairs
     return n_redo, vp
 
 
+def test_chunked_viterbi_kernel_on_short_models(engine, cpr_models, cpr_oracle, oracle):
+    """ckm_viterbi_scores mode 2: every pair through vit_kernel (shared-memory int32 rows), the kernel production keeps for
+    M > 1024 -- bit-identical to the lane-blocked kernels and to the oracle on the 43 short models."""
+    hm = synth.read_hmms(CPR_HMM)
+    res, off = _special_bin(hm, np.random.default_rng(78), n_bg=30)
+    db = engine.seqdb(res, off)
+    v32 = engine.viterbi_scores(cpr_models, db, int32_only=True)
+    vch = engine.viterbi_scores(cpr_models, db, chunked_only=True)
+    db.close()
+    assert v32.tobytes() == vch.tobytes(), np.argwhere(v32 != vch)[:5]
+    rng = np.random.default_rng(2)
+    for _ in range(1500):
+        a, s = int(rng.integers(cpr_models.n)), int(rng.integers(len(off) - 1))
+        exp = np.float32(oracle.vitfilter(cpr_oracle, a, res[off[s]:off[s + 1]]))
+        assert vch[a, s] == exp or (np.isinf(vch[a, s]) and np.isinf(exp) and np.sign(vch[a, s]) == np.sign(exp)), (a, s)
+
+
 def test_vitp_cpr43_all_pairs(engine, cpr_models, cpr_oracle, oracle):
     hm = synth.read_hmms(CPR_HMM)
     res, off = _special_bin(hm, np.random.default_rng(77))
