@@ -31,7 +31,8 @@ class Stats(C.Structure):
                 ("n_hits_seq", C.c_int64), ("n_domains", C.c_int64), ("n_reported", C.c_int64),
                 ("ms_ssv", C.c_float), ("ms_msv", C.c_float), ("ms_bias", C.c_float), ("ms_vit", C.c_float),
                 ("ms_fwd", C.c_float), ("ms_domdef", C.c_float), ("ms_total", C.c_float),
-                ("kernel_launches", C.c_int64), ("n_vit_redo", C.c_int64), ("n_queue_retries", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("n_vit_redo", C.c_int64), ("n_msv_exact", C.c_int64),
+                ("n_queue_retries", C.c_int64)]
 
 
 class QaRow(C.Structure):
@@ -64,9 +65,10 @@ class ReduceMeta(C.Structure):
 # every symbol include/ckm.h declares (tests/test_abi.py checks the .so exports each one)
 SYMBOLS = ["ckm_init", "ckm_destroy", "ckm_last_error", "ckm_version", "ckm_device_name",
            "ckm_models_load", "ckm_models_count", "ckm_models_info", "ckm_models_find", "ckm_models_select",
-           "ckm_models_write", "ckm_models_free", "ckm_digitize", "ckm_seqdb_create", "ckm_seqdb_free",
+           "ckm_models_write", "ckm_models_free", "ckm_digitize", "ckm_fasta_parse", "ckm_seqdb_create", "ckm_seqdb_free",
            "ckm_search", "ckm_search_per_bin", "ckm_hits_free", "ckm_last_stats", "ckm_msv_scores",
-           "ckm_filter_scores", "ckm_viterbi_scores", "ckm_write_domtblout", "ckm_reduce", "ckm_genome_check", "ckm_free", "ckm_allgather_qa"]
+           "ckm_filter_scores", "ckm_viterbi_scores", "ckm_write_domtblout", "ckm_reduce", "ckm_genome_check", "ckm_free", "ckm_allgather_qa", "ckm_nccl_unique_id",
+           "ckm_nccl_comm_init", "ckm_nccl_comm_destroy"]
 
 _lib = None
 
@@ -95,6 +97,7 @@ def lib():
     L.ckm_models_free.argtypes = [vp]
     L.ckm_models_free.restype = None
     L.ckm_digitize.argtypes = [C.c_char_p, i64, vp]
+    L.ckm_fasta_parse.argtypes = [C.c_char_p, i64, vp, vp, i32, vp, i64, C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]
     L.ckm_seqdb_create.argtypes = [vp, vp, vp, i32, vp, i32, C.POINTER(vp)]
     L.ckm_seqdb_free.argtypes = [vp]
     L.ckm_seqdb_free.restype = None
@@ -115,6 +118,10 @@ def lib():
     L.ckm_free.argtypes = [vp]
     L.ckm_free.restype = None
     L.ckm_allgather_qa.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
+    L.ckm_nccl_unique_id.argtypes = [vp, i32]
+    L.ckm_nccl_comm_init.argtypes = [vp, i32, i32, vp, C.POINTER(vp)]
+    L.ckm_nccl_comm_destroy.argtypes = [vp]
+    L.ckm_nccl_comm_destroy.restype = None
     _lib = L
     return L
 

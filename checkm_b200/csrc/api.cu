@@ -176,6 +176,45 @@ int ckm_digitize(const char *text, int64_t n, uint8_t *out) {
   return CKM_OK;
 }
 
+// FASTA text -> digitised residues + CSR offsets + the header lines (text after '>', joined by '\n').  A header line starts
+// with '>' at the beginning of a line; whitespace inside sequence lines is dropped; bytes before the first header are ignored.
+int ckm_fasta_parse(const char *text, int64_t n, uint8_t *residues_out, int64_t *offsets_out, int32_t max_records,
+                    char *headers_out, int64_t headers_cap, int32_t *nrec_out, int64_t *nres_out, int64_t *hdr_bytes_out) {
+  if ((!text && n > 0) || !residues_out || !offsets_out || !headers_out || !nrec_out || !nres_out || !hdr_bytes_out) { set_error("ckm_fasta_parse: bad argument"); return CKM_EINVAL; }
+  static uint8_t lut[256]; static bool lut_ready = false;
+  if (!lut_ready) {
+    for (int c = 0; c < 256; ++c) {
+      const bool ws = (c == ' ' || (c >= 9 && c <= 13));
+      const int d = digitize_char((unsigned char)c);
+      lut[c] = ws ? 255 : (uint8_t)(d < 0 ? 26 : d);      // 255 = skip; unknown symbols become X like ckm_digitize
+    }
+    lut_ready = true;
+  }
+  int32_t nrec = 0; int64_t nres = 0, hb = 0, i = 0;
+  bool started = false;
+  while (i < n) {
+    const char *nlp = (const char *)std::memchr(text + i, '\n', (size_t)(n - i));
+    const int64_t e = nlp ? (nlp - text) : n;                  // line is [i, e)
+    if (text[i] == '>') {
+      if (nrec >= max_records) { set_error("ckm_fasta_parse: more records than the caller allowed for"); return CKM_ECAPACITY; }
+      int64_t he = e;
+      if (he > i + 1 && text[he - 1] == '\r') --he;
+      const int64_t len = he - (i + 1);
+      if (hb + len + 1 > headers_cap) { set_error("ckm_fasta_parse: header buffer too small"); return CKM_ECAPACITY; }
+      if (nrec > 0) headers_out[hb++] = '\n';
+      std::memcpy(headers_out + hb, text + i + 1, (size_t)len); hb += len;
+      offsets_out[nrec++] = nres;
+      started = true;
+    } else if (started) {
+      for (int64_t j = i; j < e; ++j) { const uint8_t c = lut[(unsigned char)text[j]]; if (c != 255) residues_out[nres++] = c; }
+    }
+    i = e + 1;
+  }
+  offsets_out[nrec] = nres;
+  *nrec_out = nrec; *nres_out = nres; *hdr_bytes_out = hb;
+  return CKM_OK;
+}
+
 static inline uint8_t unbiased_byteify_h(float scale_b, float sc) {
   sc = -1.0f * roundf(scale_b * sc);
   return (sc > 255.0f) ? 255 : (uint8_t)sc;

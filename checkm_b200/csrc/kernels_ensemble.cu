@@ -421,6 +421,7 @@ int ensembles_launch(ckm_engine *e, const ckm_models *m, DomdefParams &p, const 
   CKM_CUDA(cudaMemcpyAsync(job->b_idx.p, multi_idx.data(), sizeof(int32_t) * nm, cudaMemcpyHostToDevice, st));
   CKM_CUDA(cudaMemcpyAsync(job->b_off.p, job->off.data(), sizeof(int64_t) * nm, cudaMemcpyHostToDevice, st));
   CKM_CUDA(cudaMemsetAsync(job->b_cnt.p, 0, sizeof(int32_t) * nm, st));
+  CKM_CUDA(cudaMemsetAsync(job->b_env.p, 0, sizeof(Envelope) * (size_t)nm * MAXENV, st));      // the kernel fills only the slots it uses; the whole block is copied back
   EnsembleParams ep;
   ep.d = p; ep.regions = job->b_regs.as<Region>(); ep.multi_idx = job->b_idx.as<int32_t>(); ep.nmulti = nm;
   ep.scratch_off = job->b_off.as<int64_t>(); ep.scratch = job->b_scr.as<float>(); ep.env_out = job->b_env.as<Envelope>(); ep.env_count = job->b_cnt.as<int32_t>();

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(SSV_WARPS * 32, 1) ssv_kernel(SsvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ int s_unit, s_item;
+  __shared__ int16_t su[SSV_WARPS][64];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t sel = (lane == 0) ? 0x1054u : 0x3210u;
@@ -160,6 +161,8 @@ __global__ void __launch_bounds__(SSV_WARPS * 32, 1) ssv_kernel(SsvParams p) {
         if ((m_lo | m_hi) == 0u) continue;
         if (nt > 1) { chain_cand = true; continue; }
         // which models of the tile own a firing slot?  lane j < nmodels answers for tile model j
+        su[warp][lane] = (int16_t)ulo; su[warp][32 + lane] = (int16_t)uhi;      // the 64 slot maxima, for the per-model maximum
+        __syncwarp();
         const TileDesc td = p.tiles[t];
         if (lane < td.nmodels) {
           const TileModel tm = p.tile_models[td.first_model + lane];
@@ -168,10 +171,38 @@ __global__ void __launch_bounds__(SSV_WARPS * 32, 1) ssv_kernel(SsvParams p) {
           bool act = (mask & range) != 0ull;
           if (act && p.model_active != nullptr) act = p.model_active[(int64_t)sbin * p.nmodels + tm.model] != 0;
           if (act) {
-            const int pos = atomicAdd(p.cand_count, 1);
-            if (pos < p.cand_cap) p.cand[pos] = make_int2(s, tm.model);
+            int umax = 0;
+            for (int z = tm.slot0; z < tm.slot0 + tm.nslots; ++z) umax = max(umax, (int)su[warp][z]);
+            const int jbound = min(F[tm.slot0] + tjb, I8CAP);                    // from here on J (or the int8 clamp) could have mattered
+            if (!p.resolve || umax >= jbound || umax < 1) {
+              const int pos = atomicAdd(p.cand_count, 1);
+              if (pos < p.cand_cap) p.cand[pos] = make_int2(s, tm.model);
+            } else {
+              // exact MSV score: xE_max = u_max + xB0 (u = max(sv, xB0) - xB0 and u_max >= 1), xJ = max(xE_max - tec, 0)
+              const ModelScalars ms = p.ms[tm.model];
+              const int tjbm = min(tjb + (int)ms.tbm_b, 255);
+              const int xB0 = max((int)ms.base_b - tjbm, 0);
+              const int xJ = max(umax + xB0 - (int)ms.tec_b, 0);
+              float usc = ((float)(xJ - tjb) - (float)ms.base_b);
+              usc = __fdiv_rn(usc, ms.scale_b);
+              usc = __fsub_rn(usc, 3.0f);
+              if (p.xj_dense != nullptr) p.xj_dense[(int64_t)p.model_slot[tm.model] * p.nseq + s] = xJ;
+              const float nullsc = p.nullsc[s];
+              const float seq_score = __fdiv_rn(__fsub_rn(usc, nullsc), 0.69314718055994529f);
+              const double P = gumbel_surv((double)seq_score, (double)ms.evparam[0], (double)ms.evparam[1]);
+              atomicAdd(p.resolved_count, 1);
+              if (P <= p.F1) {
+                const int pos = atomicAdd(p.pass_count, 1);
+                if (pos < p.pass_cap) {
+                  Candidate cd;
+                  cd.seq = s; cd.model = tm.model; cd.usc = usc; cd.filtersc = nullsc; cd.vitsc = 0.f; cd.fwdsc = 0.f; cd.P = P;
+                  p.pass[pos] = cd;
+                }
+              }
+            }
           }
         }
+        __syncwarp();
       }
       if (nt > 1 && chain_cand && lane == 0) {
         const TileModel tm = p.tile_models[p.tiles[t0].first_model];

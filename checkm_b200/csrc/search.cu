@@ -24,7 +24,7 @@ static bool use_blocked_kernels();
 static bool use_packed_viterbi() { const char *v = std::getenv("CKM_VITP"); return use_blocked_kernels() && !(v != nullptr && v[0] == '0'); }
 static int fan_out(ckm_engine *e);
 static int fan_in(ckm_engine *e);
-enum { CTR_UNIT4 = 0, CTR_UNIT8, CTR_UNIT16, CTR_UNIT32, CTR_CAND, CTR_MSV, CTR_BIAS, CTR_VIT, CTR_FWD, CTR_ENV, CTR_DOM, CTR_VREDO, CTR_N = 32 };
+enum { CTR_UNIT4 = 0, CTR_UNIT8, CTR_UNIT16, CTR_UNIT32, CTR_CAND, CTR_MSV, CTR_BIAS, CTR_VIT, CTR_FWD, CTR_ENV, CTR_DOM, CTR_VREDO, CTR_SSVRES, CTR_N = 32 };
 
 struct ActiveMasks {
   DevBuf tile_active, model_active, model_slot;
@@ -140,6 +140,12 @@ static int run_stage1(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
     p.cand = s1.cand.as<int2>(); p.cand_count = e->d_counters + CTR_CAND; p.cand_cap = s1.cand_cap;
     p.bnd = need_bnd ? s1.bnd.as<int16_t>() : nullptr; p.bnd_stride = bnd_stride;
     p.cells = s1.cells.as<unsigned long long>();
+    { const char *v = std::getenv("CKM_SSV_RESOLVE"); p.resolve = (v != nullptr && v[0] == '0') ? 0 : 1; }
+    p.ms = m->d_scalars; p.nullsc = db->d_nullsc;
+    p.pass = s1.pass.as<Candidate>(); p.pass_count = e->d_counters + CTR_MSV; p.pass_cap = s1.pass_cap;
+    p.resolved_count = e->d_counters + CTR_SSVRES;
+    p.xj_dense = xj_dense; p.model_slot = am.model_slot.as<int32_t>();
+    p.F1 = 0.02;
     int64_t maxbytes = 0;
     for (int g : gl[c]) maxbytes = std::max<int64_t>(maxbytes, m->groups[g].table_bytes);
     const int64_t units = (int64_t)p.ngroups * p.nchunks;
@@ -275,7 +281,7 @@ int ckm_filter_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_i
   if (!pass1.empty()) CKM_CUDA(cudaMemcpy(pass1.data(), s1.pass.p, sizeof(Candidate) * pass1.size(), cudaMemcpyDeviceToHost));
   for (const Candidate &c : pass1) passed_out[(int64_t)slot[c.model] * db->nseq + c.seq] |= 1;
   e->stats.n_pairs = n;
-  e->stats.n_ssv_cand = ctr[CTR_CAND]; e->stats.n_past_msv = ctr[CTR_MSV]; e->stats.n_past_bias = ctr[CTR_BIAS];
+  e->stats.n_ssv_cand = (int64_t)ctr[CTR_CAND] + ctr[CTR_SSVRES]; e->stats.n_msv_exact = ctr[CTR_CAND]; e->stats.n_past_msv = ctr[CTR_MSV]; e->stats.n_past_bias = ctr[CTR_BIAS];
   e->stats.n_past_vit = ctr[CTR_VIT]; e->stats.n_past_fwd = ctr[CTR_FWD]; e->stats.n_vit_redo = ctr[CTR_VREDO];
   cudaEventElapsedTime(&e->stats.ms_ssv, e->ev[0], e->ev[1]);
   cudaEventElapsedTime(&e->stats.ms_msv, e->ev[1], e->ev[2]);
@@ -393,7 +399,7 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
   }
   tr.mark("filters done");
   e->stats.n_pairs = n_pairs; e->stats.n_cells = (int64_t)cells;
-  e->stats.n_ssv_cand = ctr[CTR_CAND]; e->stats.n_past_msv = ctr[CTR_MSV]; e->stats.n_past_bias = ctr[CTR_BIAS];
+  e->stats.n_ssv_cand = (int64_t)ctr[CTR_CAND] + ctr[CTR_SSVRES]; e->stats.n_msv_exact = ctr[CTR_CAND]; e->stats.n_past_msv = ctr[CTR_MSV]; e->stats.n_past_bias = ctr[CTR_BIAS];
   e->stats.n_past_vit = ctr[CTR_VIT]; e->stats.n_past_fwd = ctr[CTR_FWD]; e->stats.n_vit_redo = ctr[CTR_VREDO];
   const int npairs = ctr[CTR_FWD];
   std::vector<Candidate> fl((size_t)npairs);
@@ -786,7 +792,7 @@ int ckm_msv_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_idx,
   CKM_CUDA(cudaStreamSynchronize(e->stream));
   if (ctr[CTR_CAND] > s1.cand_cap || ctr[CTR_MSV] > s1.pass_cap) { set_error("candidate queue overflow"); return CKM_ECAPACITY; }
   e->stats.n_pairs = n; e->stats.n_cells = (int64_t)cells;
-  e->stats.n_ssv_cand = ctr[CTR_CAND]; e->stats.n_past_msv = ctr[CTR_MSV];
+  e->stats.n_ssv_cand = (int64_t)ctr[CTR_CAND] + ctr[CTR_SSVRES]; e->stats.n_msv_exact = ctr[CTR_CAND]; e->stats.n_past_msv = ctr[CTR_MSV];
   cudaEventElapsedTime(&e->stats.ms_ssv, e->ev[0], e->ev[1]);
   cudaEventElapsedTime(&e->stats.ms_msv, e->ev[1], e->ev[2]);
   return CKM_OK;

@@ -27,6 +27,15 @@ struct SsvParams {
   int2 *cand; int32_t *cand_count; int32_t cand_cap;
   int16_t *bnd; int64_t bnd_stride;   // per-warp boundary columns for chained tiles (2 buffers of bnd_stride each)
   unsigned long long *cells;          // statistics: DP cells swept
+  // Resolving a pair in the SSV epilogue: while the J state cannot have fired (u_max below the J bound and the int8 cap) the
+  // maximum of the sweep IS the MSV filter's xE, so the exact score and its P-value follow from u_max alone and the pair goes
+  // straight to the pass list; only J-eligible / capped / chained pairs are forwarded to the exact MSV kernels.
+  int32_t resolve;                    // 1: resolve in the epilogue (CKM_SSV_RESOLVE=0 forwards every firing pair, as a cross-check)
+  const ModelScalars *ms; const float *nullsc;
+  Candidate *pass; int32_t *pass_count; int32_t pass_cap;
+  int32_t *resolved_count;            // pairs scored here (statistics)
+  int32_t *xj_dense; const int32_t *model_slot;   // parity output (see MsvParams)
+  double F1;
 };
 
 int launch_ssv(int J, const SsvParams &p, int grid, size_t smem_bytes, cudaStream_t stream);

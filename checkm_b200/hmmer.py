@@ -135,22 +135,33 @@ def write_domtblout(models, hits, bin_index, seq_base, names, descs, path):
 
 
 def write_sidecar(table_path, hits, names, descs, models):
-    """Binary companion of a domtblout file: the same rows as ckm_hit records plus the name tables they index."""
+    """Binary companion of a domtblout file: the same rows as ckm_hit records, plus the names/descriptions of the target
+    sequences and the (name, accession) of the queries that occur in them (rows re-indexed into those two tables)."""
     info = models.info()
     used = np.unique(hits['model']) if len(hits) else np.zeros(0, dtype=np.int32)
-    remap = {int(m): i for i, m in enumerate(used)}
+    useq = np.unique(hits['seq']) if len(hits) else np.zeros(0, dtype=np.int32)
     rows = hits.copy()
     if len(rows):
-        rows['model'] = np.asarray([remap[int(m)] for m in rows['model']], dtype=np.int32)
-    np.savez(table_path + '.ckm.npz', hits=rows, names=np.asarray(names, dtype=object), descs=np.asarray(descs, dtype=object),
-             qnames=np.asarray([info[int(m)].name.decode() for m in used], dtype=object),
-             qaccs=np.asarray([info[int(m)].acc.decode() for m in used], dtype=object), allow_pickle=True)
+        rows['model'] = np.searchsorted(used, rows['model']).astype(np.int32)
+        rows['seq'] = np.searchsorted(useq, rows['seq']).astype(np.int32)
+
+    def blob(items):
+        return np.frombuffer('\n'.join(items).encode('utf-8', 'replace'), dtype=np.uint8)
+    with open(table_path + '.ckm.npz', 'wb') as f:
+        np.savez(f, hits=rows, names=blob(names[int(i)] for i in useq), descs=blob(descs[int(i)].replace('\n', ' ') for i in useq),
+                 qnames=blob(info[int(m)].name.decode() for m in used), qaccs=blob(info[int(m)].acc.decode() for m in used))
 
 
 def read_sidecar(table_path):
-    z = np.load(table_path + '.ckm.npz', allow_pickle=True)
-    qids = [(n, a if a else '-') for n, a in zip(z['qnames'].tolist(), z['qaccs'].tolist())]
-    return z['hits'], z['names'].tolist(), z['descs'].tolist(), qids
+    def lines(a, n):
+        return a.tobytes().decode('utf-8', 'replace').split('\n') if n else []
+    with np.load(table_path + '.ckm.npz') as z:
+        hits = z['hits']
+        nseq = int(hits['seq'].max()) + 1 if len(hits) else 0
+        nq = int(hits['model'].max()) + 1 if len(hits) else 0
+        names, descs = lines(z['names'], nseq), lines(z['descs'], nseq)
+        qids = [(n, a if a else '-') for n, a in zip(lines(z['qnames'], nq), lines(z['qaccs'], nq))]
+    return hits, names, descs, qids
 
 
 class HMMERParser(object):

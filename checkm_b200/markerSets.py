@@ -155,6 +155,21 @@ class MarkerSet(object):
         return 100 * comp / len(self.markerSet), 100 * cont / len(self.markerSet)
 
 
+_ACC_CACHE = {}
+
+
+def _hmm_file_accessions(markerFile):
+    """Accessions of an HMM file as HmmModelParser.parse() yields them (markerSets.py:265-270), read once per file version:
+    the reference re-parses the file on every call, which for a 5,000-model file costs more than searching a bin."""
+    key = (os.path.abspath(markerFile), os.path.getmtime(markerFile), os.path.getsize(markerFile))
+    accs = _ACC_CACHE.get(key)
+    if accs is None:
+        accs = [model.acc for model in HmmModelParser(markerFile).parse()]
+        _ACC_CACHE.clear()
+        _ACC_CACHE[key] = accs
+    return accs
+
+
 class MarkerSetParser(object):
     def __init__(self, threads=1):
         self.logger = logging.getLogger('timestamp')
@@ -172,10 +187,7 @@ class MarkerSetParser(object):
         elif kind == BinMarkerSets.TREE_MARKER_SET:
             result = self.parseLineageMarkerSetFile(markerFile)
         else:
-            everything = [set()]
-            for model in HmmModelParser(markerFile).parse():
-                everything[0].add(model.acc)
-            single = MarkerSet(0, "N/A", -1, everything)
+            single = MarkerSet(0, "N/A", -1, [set(_hmm_file_accessions(markerFile))])
             for binId in binIds:
                 bms = BinMarkerSets(binId, BinMarkerSets.HMM_MODELS_SET)
                 bms.addMarkerSet(single)

@@ -206,8 +206,11 @@ class ResultsParser(object):
     def _reduce(self, binIds, tables, bIgnoreThresholds, evalueThreshold, lengthThreshold, bSkipPseudo, bSkipAdj):
         # global model table = every accession of every bin's model dict
         accs, acc_idx = [], {}
+        distinct = {}                           # bins usually share one model dict (HMM file, taxon file): visit it once
         for binId in binIds:
-            for acc in self.models[binId]:
+            distinct.setdefault(id(self.models[binId]), self.models[binId])
+        for md in distinct.values():
+            for acc in md:
                 if acc not in acc_idx:
                     acc_idx[acc] = len(accs)
                     accs.append(acc)
@@ -215,8 +218,8 @@ class ResultsParser(object):
         has = np.zeros((nm, 3), dtype=np.int32)
         cut = np.zeros((nm, 6), dtype=np.float64)
         is_tigr = np.zeros(nm, dtype=np.uint8)
-        for binId in binIds:
-            for acc, model in self.models[binId].items():
+        for md in distinct.values():
+            for acc, model in md.items():
                 i = acc_idx[acc]
                 for z, attr in enumerate(('ga', 'tc', 'nc')):
                     v = getattr(model, attr, None)
@@ -240,10 +243,10 @@ class ResultsParser(object):
             bases[binId] = seq_base
             if parsed is not None:
                 any_text = True
-                text_scores.extend((h.full_score, h.dom_score) for h in parsed)
+                text_scores.append(np.asarray([(h.full_score, h.dom_score) for h in parsed], dtype=np.float64).reshape(-1, 2))
                 parsed_all.extend(parsed)
-            else:
-                text_scores.extend((float('%6.1f' % r['full_score']), float('%6.1f' % r['dom_score'])) for r in rows)
+            else:                               # binary rows: the same rounding the text round trip applies, vectorised
+                text_scores.append(np.rint(np.stack([rows['full_score'], rows['dom_score']], axis=1).astype(np.float64) * 10.0) / 10.0)
                 parsed_all.extend([None] * len(rows))
             order = {n: r for r, n in enumerate(sorted(set(names)))}
             for n in names:
@@ -296,7 +299,7 @@ class ResultsParser(object):
         meta.name_rank = name_rank.ctypes.data if nseq else None
         meta.has_cut = has.ctypes.data
         meta.cutoffs = cut.ctypes.data
-        row_scores = np.asarray(text_scores, dtype=np.float64).reshape(-1, 2) if (any_text and len(hits)) else None
+        row_scores = np.ascontiguousarray(np.concatenate(text_scores)) if (any_text and len(hits)) else None
         meta.row_scores = row_scores.ctypes.data if row_scores is not None else None
         qa = C.POINTER(_lib.QaRow)()
         nqa = C.c_int32()
@@ -321,6 +324,9 @@ class ResultsParser(object):
         for b, binId in enumerate(binIds):
             rows, names, descs, qids, _parsed = tables[binId]
             base = bases[binId]
+            qname_of = {}
+            for qn, qa_ in qids:
+                qname_of.setdefault(qa_ if qa_ not in ('-', '') else qn, qn)
             groups, keys = {}, {}
             for pos, rec in enumerate(per_bin.get(b, [])):
                 acc = accs[int(rec['model'])]
@@ -330,11 +336,7 @@ class ResultsParser(object):
                     keys[acc] = (0, pos) if dk < 0 else (1, dk)
                 src = harr[int(rec['src_row'])]
                 a = int(rec['seq_a']) - base
-                qname = None
-                for qn, qa_ in qids:
-                    if (qa_ if qa_ not in ('-', '') else qn) == acc:
-                        qname = qn
-                        break
+                qname = qname_of.get(acc)
                 original = parsed_all[int(rec['src_row'])]
                 if original is not None:
                     hit = MarkerHit()

@@ -73,7 +73,7 @@ typedef struct {
 typedef struct {
   int64_t n_pairs;        /* (ORF x HMM) pairs scored by the SSV/MSV stage    */
   int64_t n_cells;        /* sum of L*M over those pairs                      */
-  int64_t n_ssv_cand;     /* pairs the SSV pre-filter forwards to exact MSV   */
+  int64_t n_ssv_cand;     /* pairs the SSV pre-filter fires on (scored exactly, in its epilogue or by the exact MSV kernels) */
   int64_t n_past_msv, n_past_bias, n_past_vit, n_past_fwd;
   int64_t n_hits_seq;     /* targets in the hit list (before E thresholds)    */
   int64_t n_domains;      /* domains defined                                  */
@@ -81,6 +81,7 @@ typedef struct {
   float   ms_ssv, ms_msv, ms_bias, ms_vit, ms_fwd, ms_domdef, ms_total;   /* CUDA-event times of the last search */
   int64_t kernel_launches;
   int64_t n_vit_redo;     /* pairs the packed Viterbi kernel handed to the int32 kernel (strong hits, guard conditions) */
+  int64_t n_msv_exact;    /* of n_ssv_cand, the pairs forwarded to the exact MSV kernels (J-eligible, capped, chained) */
   int64_t n_queue_retries;/* times the filter cascade was re-run with larger candidate queues (candidate-dense input) */
 } ckm_stats;
 
@@ -130,6 +131,11 @@ void ckm_models_free(ckm_models *m);
 /* ---- sequences: digitised residues (codes 0..28 of "ACDEFGHIKLMNPQRSTVWY-BJZOUX*~"), CSR offsets,
  *      bin id per sequence.  Replaces hmmsearch's reading of <seqfile> (genes.faa). ---- */
 int  ckm_digitize(const char *text, int64_t n, uint8_t *out);    /* ASCII -> codes; returns #unknown symbols via negative? no: 0 */
+/* a whole protein FASTA file (genes.faa, checkm/markerGeneFinder.py:113-127) in one pass: residue codes, CSR offsets
+ * (max_records + 1 entries) and the header lines (text after '>', joined by '\n') from which the caller takes names and
+ * descriptions.  residues_out needs n bytes, headers_out at most n. */
+int  ckm_fasta_parse(const char *text, int64_t n, uint8_t *residues_out, int64_t *offsets_out, int32_t max_records,
+                     char *headers_out, int64_t headers_cap, int32_t *nrec_out, int64_t *nres_out, int64_t *hdr_bytes_out);
 int  ckm_seqdb_create(ckm_engine *e, const uint8_t *residues, const int64_t *seq_offsets, int32_t nseq,
                       const int32_t *bin_of_seq, int32_t nbins, ckm_seqdb **out);
 void ckm_seqdb_free(ckm_seqdb *db);
@@ -220,8 +226,14 @@ int  ckm_genome_check(ckm_engine *e, int32_t nbins, const int64_t *bin_set_off, 
                       const int32_t *marker_count, int32_t individual_markers, ckm_qa_row *rows_out);
 void ckm_free(void *p);
 
-/* ---- multi-GPU: all-gather of the fixed-width QA rows over NCCL (config #4).  comm is an ncclComm_t
- * created by the caller (torch.distributed's, or ncclCommInitRank); rows_out holds world*nrows_max rows. */
+/* ---- multi-GPU (BASELINE.json configs[3] "NCCL gather of qa table"): bins are sharded over ranks, one
+ * process per GPU; the only inter-GPU traffic is one ncclAllGather of the fixed-width QA rows.  The communicator is the
+ * caller's (an ncclComm_t from ncclCommInitRank) or one made here: rank 0 calls ckm_nccl_unique_id, ships the 128 bytes to
+ * the other ranks by whatever channel it has (MPI, torch.distributed, a file), every rank calls ckm_nccl_comm_init.
+ * rows_out holds world * nrows_max rows (rank r's rows start at r * nrows_max), counts_out the row count of every rank. ---- */
+int  ckm_nccl_unique_id(uint8_t *id_out, int32_t nbytes);
+int  ckm_nccl_comm_init(ckm_engine *e, int32_t world, int32_t rank, const uint8_t *id, void **comm_out);
+void ckm_nccl_comm_destroy(void *comm);
 int  ckm_allgather_qa(ckm_engine *e, void *nccl_comm, const ckm_qa_row *rows, int32_t nrows, int32_t nrows_max,
                       int32_t world, ckm_qa_row *rows_out, int32_t *counts_out);
 

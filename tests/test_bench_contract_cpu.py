@@ -20,11 +20,12 @@ def test_reference_arm_json_line():
         assert k in d, k
     assert d['impl'] == 'reference' and d['metric'] == 'genomes/hour' and d['unit'] == 'genomes/hour'
     assert d['higher_is_better'] is True and d['vs_baseline'] is None and d['value'] > 0
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['cpu_baseline']['kind'] in ('port', 'hmmer') and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {"value": d['value'], "unit": d['unit'], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     sys.path.insert(0, ROOT)
     import bench
-    assert d['config']['workload'] == bench.workload_name(bench.total_model_positions(bench.model_db()[0]))
+    assert d['config']['workload'] == bench.workload_name(3, bench.total_model_positions(bench.model_db()))
+    assert 'no extrapolation' in d['cpu_baseline']['sample'] and d['cpu_baseline']['gcups_per_core'] > 0
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -23,10 +23,10 @@ FIELDS = ('seq', 'tlen', 'qlen', 'dom', 'ndom', 'hmm_from', 'hmm_to', 'ali_from'
 
 @pytest.fixture(scope='module')
 def big(engine):
-    db_path, plant = bench.model_db('_test')
+    db_path = bench.model_db(bench.N_MODELS)
     models = engine.load_models(db_path)
-    hm = synth.read_hmms(plant)
-    bins = [synth.make_bin('fs%d' % i, hm, seed=4200 + i, n_orfs=bench.ORFS_PER_BIN, copies=(0, 1, 1, 1, 2)) for i in range(2)]
+    hm = synth.read_hmms(bench.CPR)
+    bins = [synth.make_bin('fs%d' % i, hm, seed=4200 + i, n_orfs=bench.CFG[3]['orfs'], copies=(0, 1, 1, 1, 2)) for i in range(2)]
     yield models, bins
     models.close()
 
@@ -47,7 +47,7 @@ def _search(engine, models, bins):
 def test_fullsize_replicas_split_determinism(engine, big):
     models, bins = big
     hits, st = _search(engine, models, bins)
-    assert st.n_pairs == 2 * bench.ORFS_PER_BIN * models.n
+    assert st.n_pairs == 2 * bench.CFG[3]['orfs'] * models.n
     # cascade fractions: the MSV filter lets through P <= 0.02 of a null-dominated workload (plus the planted homologs)
     assert 0.015 < st.n_past_msv / st.n_pairs < 0.03, st.n_past_msv / st.n_pairs
     assert st.n_past_vit / st.n_pairs < 0.004 and st.n_past_fwd / st.n_pairs < 0.001
