@@ -358,6 +358,7 @@ def main():
     ap.add_argument('--bins-per-step', type=int, default=BINS_PER_STEP)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-plugin', action='store_true', help='skip the files-on-disk plug-in path measurement')
+    ap.add_argument('--profile-plugin', action='store_true', help='cProfile of the plug-in path host code (stderr)')
     ap.add_argument('--pipeline', type=int, default=2, help='batches in flight per GPU (one engine + host thread each)')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -766,6 +767,14 @@ def plugin_path(args, batches, db_path, models):
             stage[k] += v
         return len(binIds)
     run('warm', 1)
+    if args.profile_plugin:
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        run('prof', 1)
+        pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats('cumulative').print_stats(28)
     for k in stage:
         stage[k] = 0.0
     torch.cuda.synchronize()

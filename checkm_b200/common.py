@@ -1,51 +1,54 @@
-"""Small path helpers used by the hot path (same behaviour as checkm/common.py)."""
-import errno
+"""Path and stdout helpers the hot-path classes call (behaviour of the same-named functions of checkm/common.py: same log
+messages, same exit codes).  When CheckM itself is importable its own helpers are used, so a drop-in shares one copy."""
 import logging
 import os
 import sys
 
-
-def checkFileExists(inputFile):
-    if not os.path.exists(inputFile):
-        logging.getLogger('timestamp').error('Input file does not exists: ' + inputFile + '\n')
+try:                                              # inside a CheckM install: CheckM's own helpers
+    from checkm.common import (checkFileExists, makeSurePathExists, binIdFromFilename,       # noqa: F401
+                               reassignStdOut, restoreStdOut)
+except Exception:                                 # stand-alone
+    def _fatal(message):
+        logging.getLogger('timestamp').error(message + '\n')
         sys.exit(1)
 
+    def checkFileExists(inputFile):
+        if os.path.exists(inputFile):
+            return
+        _fatal('Input file does not exists: ' + inputFile)
 
-def makeSurePathExists(path):
-    if not path:
-        return
-    try:
-        os.makedirs(path)
-    except OSError as exc:
-        if exc.errno != errno.EEXIST:
-            logging.getLogger('timestamp').error('Specified path does not exist: ' + path + '\n')
-            sys.exit(1)
+    def makeSurePathExists(path):
+        if path:
+            try:
+                os.makedirs(path, exist_ok=True)
+            except OSError:
+                _fatal('Specified path does not exist: ' + path)
 
+    def binIdFromFilename(filename):
+        """File name without directory, without a trailing .gz, without its last extension."""
+        base = os.path.basename(filename)
+        base = base[:-3] if base.endswith('.gz') else base
+        return os.path.splitext(base)[0]
 
-def binIdFromFilename(filename):
-    """Bin id = file name without directory and without its last extension (a trailing .gz is dropped first)."""
-    binId = os.path.basename(filename)
-    if binId.endswith('.gz'):
-        binId = binId[0:-3]
-    return os.path.splitext(binId)[0]
+    class _Redirect(object):
+        """stdout diverted into a file for the duration of a report (printSummary's outFile argument)."""
+        def __init__(self, path):
+            self.previous = sys.stdout
+            self.handle = open(path, 'w')
+            sys.stdout = self.handle
 
+        def undo(self):
+            self.handle.close()
+            sys.stdout = self.previous
 
-def reassignStdOut(outFile):
-    oldStdOut = sys.stdout
-    if outFile != '':
+    def reassignStdOut(outFile):
+        if outFile == '':
+            return sys.stdout
         try:
-            sys.stdout = open(outFile, 'w')
+            return _Redirect(outFile)
         except IOError:
-            logging.getLogger('timestamp').error('Error diverting stdout to file: ' + outFile)
-            sys.exit(1)
-    return oldStdOut
+            _fatal('Error diverting stdout to file: ' + outFile)
 
-
-def restoreStdOut(outFile, oldStdOut):
-    if outFile != '':
-        try:
-            sys.stdout.close()
-            sys.stdout = oldStdOut
-        except IOError:
-            logging.getLogger('timestamp').error('Error restoring stdout: ' + outFile)
-            sys.exit(1)
+    def restoreStdOut(outFile, oldStdOut):
+        if outFile != '' and isinstance(oldStdOut, _Redirect):
+            oldStdOut.undo()

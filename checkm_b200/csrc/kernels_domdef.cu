@@ -285,6 +285,9 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) envelope_kernel(DomdefParams p
         if (s1 == ST_M) {
           if (!have_last || s0 == ST_E) { lastMi = i; lastMk = k; have_last = true; }
           firstMi = i; firstMk = k;
+          if (p.trace != nullptr && lane == 0) p.trace[pw.row_off + env.i - 1 + i] = k;
+        } else if (s1 == ST_I) {
+          if (p.trace != nullptr && lane == 0) p.trace[pw.row_off + env.i - 1 + i] = -k;
         }
         if ((s1 == ST_N || s1 == ST_J || s1 == ST_C) && s1 == s0) i--;
         s0 = s1;

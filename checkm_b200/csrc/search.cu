@@ -334,6 +334,77 @@ static std::vector<float> &logsum_table() {
   return t;
 }
 
+
+// Envelope rescoring in waves: 2 matrices + specials of scratch per envelope under a fixed budget, every class on its own
+// stream.  leave_last: the last wave is left running on the class streams (the caller joins them with fan_in).
+struct EnvRunner {
+  ckm_engine *e; const ckm_models *m; DomdefParams *p; const std::vector<PairWork> *pairs; DevBuf *dscratch;
+  int64_t budget0;       // floats
+  int64_t cur_alloc;
+  int nsm;
+};
+static int64_t env_scratch_budget() {
+  // fixed scratch budget (the cached pool is reused by every later search): 60% of the device shared by the live engines,
+  // at most 56 GiB each
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  (void)free_b;
+  const size_t neng = (size_t)std::max(1, g_live_engines.load());
+  return (int64_t)std::min<size_t>(total_b * 6 / 10 / neng, (size_t)56 << 30) / (int64_t)sizeof(float);
+}
+static int run_envelope_waves(EnvRunner &R, std::vector<Envelope> &ev, DevBuf &d_ev, DevBuf &d_ord, bool leave_last) {
+  if (ev.empty()) return CKM_OK;
+  ckm_engine *e = R.e; const ckm_models *m = R.m; DomdefParams &p = *R.p; const std::vector<PairWork> &pairs = *R.pairs;
+  cudaStream_t st = e->stream;
+  const int nsm = R.nsm;
+  int rc2;
+  std::vector<int64_t> need(ev.size());
+  std::vector<int8_t> ecls(ev.size());
+  for (size_t i = 0; i < ev.size(); ++i) {
+    const PairWork &pw = pairs[ev[i].pair];
+    const int64_t Ld = ev[i].j - ev[i].i + 1, Mpad = ((m->models[pw.model].M + 1) + 31) / 32 * 32 + 32;
+    const int64_t vq = p.use_blk ? vq_of(m->models[pw.model].M) : 0;
+    const int64_t width = vq ? 32 * vq : Mpad;
+    need[i] = 2 * (Ld + 1) * 3 * width + (Ld + 1) * 15 + 64;
+    ecls[i] = (int8_t)cls_of(m->models[pw.model].M, p.use_blk != 0);
+  }
+  const int64_t budget = std::max<int64_t>(R.budget0, *std::max_element(need.begin(), need.end()));
+  if ((rc2 = d_ev.alloc(sizeof(Envelope) * ev.size())) || (rc2 = d_ord.alloc(sizeof(int32_t) * ev.size()))) return rc2;
+  std::vector<int32_t> eorder(ev.size());
+  size_t w0 = 0;
+  while (w0 < ev.size()) {
+    size_t w1 = w0; int64_t tot = 0;
+    while (w1 < ev.size() && (w1 == w0 || tot + need[w1] <= budget)) { ev[w1].scratch_off = tot; tot += need[w1]; ++w1; }
+    if (tot > R.cur_alloc) { if ((rc2 = R.dscratch->alloc(sizeof(float) * (size_t)tot))) return rc2; R.cur_alloc = tot; }
+    // this wave's envelopes grouped by class, largest first; one stream per class
+    for (size_t i = w0; i < w1; ++i) eorder[i] = (int32_t)i;
+    std::stable_sort(eorder.begin() + w0, eorder.begin() + w1, [&](int32_t a, int32_t b) { return ecls[a] != ecls[b] ? ecls[a] > ecls[b] : need[a] > need[b]; });
+    CKM_CUDA(cudaMemcpyAsync(d_ev.as<Envelope>() + w0, ev.data() + w0, sizeof(Envelope) * (w1 - w0), cudaMemcpyHostToDevice, st));
+    CKM_CUDA(cudaMemcpyAsync(d_ord.as<int32_t>() + w0, eorder.data() + w0, sizeof(int32_t) * (w1 - w0), cudaMemcpyHostToDevice, st));
+    p.envs = d_ev.as<Envelope>(); p.env_order = d_ord.as<int32_t>(); p.scratch = R.dscratch->as<float>();
+    if ((rc2 = fan_out(e))) return rc2;
+    size_t b0 = w0;
+    while (b0 < w1) {
+      size_t b1 = b0; const int c = ecls[eorder[b0]];
+      while (b1 < w1 && ecls[eorder[b1]] == c) ++b1;
+      p.env_begin = (int32_t)b0; p.env_end = (int32_t)b1;
+      const int cnt = (int)(b1 - b0);
+      if (c < N_BLK_CLASSES) rc2 = launch_envelopes2(p, c, std::min<int>(nsm * 8, (cnt + 3) / 4), e->cls[c]);
+      else rc2 = launch_envelopes(p, std::min<int>(nsm * 4, (cnt + FWD_WARPS - 1) / FWD_WARPS), e->cls[c]);
+      if (rc2) return rc2;
+      e->stats.kernel_launches++;
+      b0 = b1;
+    }
+    CKM_CUDA(cudaStreamSynchronize(st));          // the two copies above have read the host vectors
+    if (w1 < ev.size() || !leave_last) {
+      if ((rc2 = fan_in(e))) return rc2;
+      CKM_CUDA(cudaStreamSynchronize(st));
+    }
+    w0 = w1;
+  }
+  return CKM_OK;
+}
+
 struct HostHit { int pair; HitOut h; int first_dom, ndom_slots; };
 
 // CKM_TRACE=1: host-side wall-clock marks of one search on stderr (where the time between the CUDA events goes)
@@ -496,65 +567,8 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
       CKM_CUDA(cudaMemsetAsync(ddoms.p, 0, sizeof(DomainOut) * (size_t)nslots, st));
       CKM_CUDA(cudaMemcpyAsync(dpairs.p, pairs.data(), sizeof(PairWork) * pairs.size(), cudaMemcpyHostToDevice, st));
       p.doms = ddoms.as<DomainOut>();
-      size_t free_b = 0, total_b = 0;
-      cudaMemGetInfo(&free_b, &total_b);
-      (void)free_b;
-      // fixed scratch budget (the cached pool is reused by every later search): 60% of the device shared by the live engines,
-      // at most 56 GiB each
-      const size_t neng = (size_t)std::max(1, g_live_engines.load());
-      const int64_t budget0 = (int64_t)std::min<size_t>(total_b * 6 / 10 / neng, (size_t)56 << 30) / (int64_t)sizeof(float);
-      int64_t cur_alloc = 0;
-      // Rescores a batch of envelopes: 2 matrices + specials of scratch each, in waves under the budget, every class on its
-      // own stream.  leave_last: the last wave is left running on the class streams (the caller joins them with fan_in).
-      auto run_env_batch = [&](std::vector<Envelope> &ev, DevBuf &d_ev, DevBuf &d_ord, bool leave_last) -> int {
-        if (ev.empty()) return CKM_OK;
-        int rc2;
-        std::vector<int64_t> need(ev.size());
-        std::vector<int8_t> ecls(ev.size());
-        for (size_t i = 0; i < ev.size(); ++i) {
-          const PairWork &pw = pairs[ev[i].pair];
-          const int64_t Ld = ev[i].j - ev[i].i + 1, Mpad = ((m->models[pw.model].M + 1) + 31) / 32 * 32 + 32;
-          const int64_t vq = p.use_blk ? vq_of(m->models[pw.model].M) : 0;
-          const int64_t width = vq ? 32 * vq : Mpad;
-          need[i] = 2 * (Ld + 1) * 3 * width + (Ld + 1) * 15 + 64;
-          ecls[i] = (int8_t)cls_of(m->models[pw.model].M, p.use_blk != 0);
-        }
-        const int64_t budget = std::max<int64_t>(budget0, *std::max_element(need.begin(), need.end()));
-        if ((rc2 = d_ev.alloc(sizeof(Envelope) * ev.size())) || (rc2 = d_ord.alloc(sizeof(int32_t) * ev.size()))) return rc2;
-        std::vector<int32_t> eorder(ev.size());
-        size_t w0 = 0;
-        while (w0 < ev.size()) {
-          size_t w1 = w0; int64_t tot = 0;
-          while (w1 < ev.size() && (w1 == w0 || tot + need[w1] <= budget)) { ev[w1].scratch_off = tot; tot += need[w1]; ++w1; }
-          if (tot > cur_alloc) { if ((rc2 = dscratch.alloc(sizeof(float) * (size_t)tot))) return rc2; cur_alloc = tot; }
-          // this wave's envelopes grouped by class, largest first; one stream per class
-          for (size_t i = w0; i < w1; ++i) eorder[i] = (int32_t)i;
-          std::stable_sort(eorder.begin() + w0, eorder.begin() + w1, [&](int32_t a, int32_t b) { return ecls[a] != ecls[b] ? ecls[a] > ecls[b] : need[a] > need[b]; });
-          CKM_CUDA(cudaMemcpyAsync(d_ev.as<Envelope>() + w0, ev.data() + w0, sizeof(Envelope) * (w1 - w0), cudaMemcpyHostToDevice, st));
-          CKM_CUDA(cudaMemcpyAsync(d_ord.as<int32_t>() + w0, eorder.data() + w0, sizeof(int32_t) * (w1 - w0), cudaMemcpyHostToDevice, st));
-          p.envs = d_ev.as<Envelope>(); p.env_order = d_ord.as<int32_t>(); p.scratch = dscratch.as<float>();
-          if ((rc2 = fan_out(e))) return rc2;
-          size_t b0 = w0;
-          while (b0 < w1) {
-            size_t b1 = b0; const int c = ecls[eorder[b0]];
-            while (b1 < w1 && ecls[eorder[b1]] == c) ++b1;
-            p.env_begin = (int32_t)b0; p.env_end = (int32_t)b1;
-            const int cnt = (int)(b1 - b0);
-            if (c < N_BLK_CLASSES) rc2 = launch_envelopes2(p, c, std::min<int>(nsm * 8, (cnt + 3) / 4), e->cls[c]);
-            else rc2 = launch_envelopes(p, std::min<int>(nsm * 4, (cnt + FWD_WARPS - 1) / FWD_WARPS), e->cls[c]);
-            if (rc2) return rc2;
-            e->stats.kernel_launches++;
-            b0 = b1;
-          }
-          CKM_CUDA(cudaStreamSynchronize(st));          // the two copies above have read the host vectors
-          if (w1 < ev.size() || !leave_last) {
-            if ((rc2 = fan_in(e))) return rc2;
-            CKM_CUDA(cudaStreamSynchronize(st));
-          }
-          w0 = w1;
-        }
-        return CKM_OK;
-      };
+      EnvRunner R{e, m, &p, &pairs, &dscratch, env_scratch_budget(), 0, nsm};
+      auto run_env_batch = [&](std::vector<Envelope> &ev, DevBuf &d_ev, DevBuf &d_ord, bool leave_last) -> int { return run_envelope_waves(R, ev, d_ev, d_ord, leave_last); };
       // The envelope kernels of the single-domain regions go first (class streams); the trace ensemble of the multi-domain
       // regions (one warp per region, latency-bound) is queued on its own stream and takes the SMs as they drain.  (Started
       // the other way round the two compete for the memory system and the ensemble's dependent loads take 2-3x longer.)
@@ -799,3 +813,100 @@ int ckm_msv_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_idx,
 }
 
 }  // extern "C"
+
+namespace ckm {
+
+// hmmalign: every sequence against one model, as one full-length envelope in unihit local mode (what `hmmalign` configures:
+// Forward, Backward, posterior decoding, optimal-accuracy fill and traceback); the traceback's state per residue is the output.
+// A sequence that carries a second strong copy of the domain cannot be scored as ONE unihit envelope in scaled fp32 (the
+// Backward pass overflows where the Forward pass has underflowed); such a sequence is aligned over the envelope of its
+// best-scoring domain as the search pipeline defines it, the rest of it being flank.
+static int align_pass(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, std::vector<PairWork> &pairs, std::vector<Envelope> &envs,
+                      int64_t rows, std::vector<int32_t> &trace, std::vector<DomainOut> &doms) {
+  cudaStream_t st = e->stream;
+  PoolScope pool_scope(e);
+  const int nsm = e->prop.multiProcessorCount;
+  DevBuf dpairs, dn2, dtrace, ddoms, dscratch, denvs, deorder;
+  int rc;
+  const size_t rws = (size_t)rows;
+  if ((rc = dpairs.alloc(sizeof(PairWork) * pairs.size())) || (rc = dn2.alloc(sizeof(float) * rws)) || (rc = dtrace.alloc(sizeof(int32_t) * rws)) ||
+      (rc = ddoms.alloc(sizeof(DomainOut) * pairs.size()))) return rc;
+  CKM_CUDA(cudaMemcpyAsync(dpairs.p, pairs.data(), sizeof(PairWork) * pairs.size(), cudaMemcpyHostToDevice, st));
+  CKM_CUDA(cudaMemsetAsync(dn2.p, 0, sizeof(float) * rws, st));
+  CKM_CUDA(cudaMemsetAsync(dtrace.p, 0, sizeof(int32_t) * rws, st));
+  CKM_CUDA(cudaMemsetAsync(ddoms.p, 0, sizeof(DomainOut) * pairs.size(), st));
+  DomdefParams p{};
+  p.res = db->d_res; p.off = db->d_off; p.nullsc = db->d_nullsc; p.ms = m->d_scalars; p.rfv = m->d_rfv; p.tfv = m->d_tfv;
+  p.pairs = dpairs.as<PairWork>(); p.npairs = (int32_t)pairs.size();
+  p.n2sc = dn2.as<float>(); p.trace = dtrace.as<int32_t>();
+  p.doms = ddoms.as<DomainOut>();
+  p.row_elems = ((m->maxM + 31) / 32) * 32 + 64;
+  p.tfb = m->d_tfb; p.rfb = m->d_rfb; p.use_blk = use_blocked_kernels() ? 1 : 0;
+  EnvRunner R{e, m, &p, &pairs, &dscratch, env_scratch_budget(), 0, nsm};
+  if ((rc = run_envelope_waves(R, envs, denvs, deorder, false))) return rc;
+  trace.resize(rws);
+  doms.resize(pairs.size());
+  CKM_CUDA(cudaMemcpyAsync(trace.data(), dtrace.p, sizeof(int32_t) * rws, cudaMemcpyDeviceToHost, st));
+  CKM_CUDA(cudaMemcpyAsync(doms.data(), ddoms.p, sizeof(DomainOut) * doms.size(), cudaMemcpyDeviceToHost, st));
+  CKM_CUDA(cudaStreamSynchronize(st));
+  return CKM_OK;
+}
+
+static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_idx, int32_t nmodels, const int64_t *bin_model_offsets,
+                     const ckm_seqdb *db, double Ecut, double domEcut, ckm_hit **hits_out, int64_t *nhits_out);
+
+static int do_align(ckm_engine *e, const ckm_models *m, int32_t model, const ckm_seqdb *db, int32_t *state_out, float *oasc_out) {
+  if (!e || !m || !db || !state_out) { set_error("ckm_align: bad argument"); return CKM_EINVAL; }
+  if (model < 0 || model >= (int)m->models.size()) { set_error("ckm_align: model index out of range"); return CKM_EINVAL; }
+  cudaSetDevice(e->device);
+  std::memset(&e->stats, 0, sizeof(e->stats));
+  const int nseq = db->nseq;
+  for (int64_t i = 0; i < db->nres; ++i) state_out[i] = 0;
+  if (oasc_out) for (int s = 0; s < nseq; ++s) oasc_out[s] = 0.0f;
+  std::vector<PairWork> pairs;
+  std::vector<Envelope> envs;
+  int64_t rows = 0;
+  auto add = [&](int s, int i, int j) {
+    PairWork pw{};
+    pw.seq = s; pw.model = model; pw.L = db->len[s]; pw.first_dom = (int32_t)pairs.size(); pw.ndom_slots = 1; pw.row_off = rows;
+    rows += pw.L + 1;
+    Envelope en{};
+    en.pair = (int32_t)pairs.size(); en.i = i; en.j = j; en.null2_done = 1; en.slot = (int32_t)pairs.size();
+    pairs.push_back(pw); envs.push_back(en);
+  };
+  for (int s = 0; s < nseq; ++s) if (db->len[s] > 0) add(s, 1, db->len[s]);
+  if (pairs.empty()) return CKM_OK;
+  std::vector<int32_t> trace; std::vector<DomainOut> doms;
+  int rc;
+  if ((rc = align_pass(e, m, db, pairs, envs, rows, trace, doms))) return rc;
+  auto emit = [&](const std::vector<PairWork> &pp, const std::vector<DomainOut> &dd, const std::vector<int32_t> &tr, std::vector<int> *failed) {
+    for (size_t pi = 0; pi < pp.size(); ++pi) {
+      const PairWork &pw = pp[pi];
+      if (!dd[pi].ok) { if (failed) failed->push_back(pw.seq); continue; }
+      if (oasc_out) oasc_out[pw.seq] = dd[pi].oasc;
+      int32_t *dst = state_out + (db->offsets[pw.seq] - db->offsets[0]);
+      for (int i = 1; i <= pw.L; ++i) dst[i - 1] = tr[pw.row_off + i];
+    }
+  };
+  std::vector<int> failed;
+  emit(pairs, doms, trace, &failed);
+  if (failed.empty()) return CKM_OK;
+  // the rare sequences one unihit envelope cannot hold: the envelope of the best domain the search pipeline defines
+  ckm_hit *hits = nullptr; int64_t nhits = 0;
+  if ((rc = do_search(e, m, &model, 1, nullptr, db, 1e300, 1e300, &hits, &nhits))) return rc;
+  std::vector<int> best(nseq, -1);
+  for (int64_t h = 0; h < nhits; ++h) { const int s = hits[h].seq; if (best[s] < 0 || hits[h].dom_score > hits[best[s]].dom_score) best[s] = (int)h; }
+  pairs.clear(); envs.clear(); rows = 0;
+  for (int s : failed) if (best[s] >= 0) add(s, hits[best[s]].env_from, hits[best[s]].env_to);
+  std::free(hits);
+  if (pairs.empty()) return CKM_OK;
+  if ((rc = align_pass(e, m, db, pairs, envs, rows, trace, doms))) return rc;
+  emit(pairs, doms, trace, nullptr);
+  return CKM_OK;
+}
+
+}  // namespace ckm
+
+extern "C" int ckm_align(ckm_engine *e, const ckm_models *m, int32_t model, const ckm_seqdb *db, int32_t *state_out, float *oasc_out) {
+  return ckm::do_align(e, m, model, db, state_out, oasc_out);
+}

@@ -112,6 +112,8 @@ struct DomdefParams {
   const PairWork *pairs; int32_t npairs;
   const int32_t *pair_order; int32_t pair_begin, pair_end;   // regions kernels walk pair_order[pair_begin..pair_end) (one class, longest first)
   float *xf, *xb, *btot, *etot, *mocc, *n2sc;      // per-pair arrays, indexed by row_off
+  int32_t *trace;                                  // optional (ckm_align): state of every residue in the optimal-accuracy trace, indexed like n2sc:
+                                                   //   k > 0 match state k, k < 0 insert state -k, 0 outside the aligned region
   Region *regions; int32_t *region_count; int32_t region_cap;
   const Envelope *envs; const int32_t *env_order; int32_t env_begin, env_end;   // envelope kernels walk env_order[env_begin..env_end)
   float *scratch;

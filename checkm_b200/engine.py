@@ -155,6 +155,14 @@ class Engine:
         _lib.lib().ckm_hits_free(hits)
         return arr
 
+    def align(self, models, db, model=0):
+        """Optimal-accuracy alignment of every sequence of `db` to one model (ckm_align): per-residue states (+k match,
+        -k insert, 0 flank) over the unpadded residue stream, and the optimal-accuracy score of every sequence."""
+        state = np.zeros(len(db.residues), dtype=np.int32)
+        oasc = np.zeros(db.nseq, dtype=np.float32)
+        check(_lib.lib().ckm_align(self._h, models._h, int(model), db._h, state.ctypes.data, oasc.ctypes.data))
+        return state, oasc
+
     def close(self):
         if self._h:
             _lib.lib().ckm_destroy(self._h)

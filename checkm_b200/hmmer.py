@@ -3,8 +3,8 @@
 `HMMERRunner.search` keeps the reference's signature and contract (checkm/hmmer.py:61-74): it takes an HMM file and a
 protein FASTA, writes a domtblout file at `tableOut` (and a short report at `hmmerOut`), and on failure logs and calls
 `sys.exit(rtn)`.  No `hmmsearch` process is spawned and there is no CPU fallback.  `fetch`/`index` replace
-`hmmfetch` (hmmer.py:97-129) through the engine's model database; `align`/`press` have no GPU equivalent here
-(hmmalign is row f3 of SURVEY.md section 8) and fail loudly.
+`hmmfetch` (hmmer.py:97-129) through the engine's model database; `align` replaces `hmmalign` (hmmer.py:76-95; row f3 of
+SURVEY.md section 8) with ckm_align; `press` has nothing to do.
 
 `HMMERParser` / `HmmerHitDOM` / `HmmerHitTBL` read the tabular text back exactly like hmmer.py:140-311."""
 import logging
@@ -86,10 +86,28 @@ class HMMERRunner(object):
             sys.exit(err.code)
 
     def align(self, db, query, outputFile, writeMode='>', outputFormat='PSIBLAST', trim=True):
+        """`hmmalign [--trim] --outformat <fmt> db query > outputFile` (hmmer.py:76-95): every sequence of `query` aligned to the
+        single model of `db` by optimal accuracy on the GPU (ckm_align); the alignment is written with all consensus columns."""
         if self.mode != 'align':
             raise HMMMERModeError("Mode %s not compatible with align" % self.mode)
-        self.logger.error('hmmalign is outside the B200 hot path (SURVEY.md section 8, row f3)')
-        sys.exit(1)
+        try:
+            eng = runtime.engine()
+            models = runtime.models_for(db)
+            if models.n != 1:
+                self.logger.error('hmmalign needs an HMM file with exactly one model; %s holds %d' % (db, models.n))
+                sys.exit(1)
+            names, descs, residues, offsets = read_fasta(query)
+            sdb = eng.seqdb(residues, offsets)
+            try:
+                state, _oasc = eng.align(models, sdb, 0)
+            finally:
+                sdb.close()
+            text = format_alignment(names, descs, residues, offsets, state, int(models.info()[0].M), outputFormat, trim)
+            with open(outputFile, 'a' if writeMode.strip() == '>>' else 'w') as f:
+                f.write(text)
+        except CkmError as err:
+            self.logger.error('hmmalign engine exited with code: %d (%s)' % (err.code, err))
+            sys.exit(err.code)
 
     def fetch(self, db, key, fetchFileName, bKeyFile=False):
         if self.mode != 'fetch':
@@ -119,6 +137,70 @@ class HMMERRunner(object):
         except CkmError as err:
             self.logger.error('model index exited with code: %d (%s)' % (err.code, err))
             sys.exit(err.code)
+
+
+_LETTERS = "ACDEFGHIKLMNPQRSTVWY-BJZOUX*~"
+
+
+def format_alignment(names, descs, residues, offsets, state, M, outputFormat='Pfam', trim=False):
+    """The multiple alignment `hmmalign` builds from per-sequence traces: one column per consensus (match) position, plus
+    insert columns wide enough for the longest insertion at each position (residues of an insertion split in half: left
+    half flush left, right half flush right; the N-terminal flank flush right, the C-terminal flank flush left; `--trim`
+    drops the flanks).  Match residues upper case, inserted residues lower case, '-' deletions, '.' padding.
+    Formats: Pfam / Stockholm (one block, `#=GS <name> DE`, `#=GC RF` with x on consensus columns), afa, PSIBLAST."""
+    nseq = len(names)
+    per = []                       # per sequence: (match letter per k, insert strings per k = 0..M)
+    width = [0] * (M + 1)
+    for s in range(nseq):
+        st = state[offsets[s]:offsets[s + 1]]
+        seq = ''.join(_LETTERS[c] for c in residues[offsets[s]:offsets[s + 1]])
+        match = ['-'] * (M + 1)
+        ins = [''] * (M + 1)
+        aligned = [i for i in range(len(st)) if st[i] != 0]
+        if aligned:
+            a0, a1 = aligned[0], aligned[-1]
+            for i in range(a0, a1 + 1):
+                k = int(st[i])
+                if k > 0:
+                    match[k] = seq[i].upper()
+                elif k < 0:
+                    ins[-k] += seq[i].lower()
+            if not trim:
+                ins[0], ins[M] = seq[:a0].lower(), ins[M] + seq[a1 + 1:].lower()
+        elif not trim:
+            ins[0] = seq.lower()
+        for k in range(M + 1):
+            width[k] = max(width[k], len(ins[k]))
+        per.append((match, ins))
+    rows = []
+    for match, ins in per:
+        out = ['.' * (width[0] - len(ins[0])) + ins[0]]
+        for k in range(1, M + 1):
+            out.append(match[k])
+            w, t = width[k], ins[k]
+            if k == M:
+                out.append(t + '.' * (w - len(t)))
+            else:
+                h = len(t) // 2
+                out.append(t[:h] + '.' * (w - len(t)) + t[h:])
+        rows.append(''.join(out))
+    rf = '.' * width[0] + ''.join('x' + '.' * width[k] for k in range(1, M + 1))
+    fmt = (outputFormat or 'Pfam').lower()
+    if fmt == 'afa':
+        return ''.join('>%s%s\n%s\n' % (n, (' ' + d) if d else '', r) for n, d, r in zip(names, descs, rows))
+    if fmt == 'psiblast':
+        pad = max([len(n) for n in names] + [1])
+        return ''.join('%-*s  %s\n' % (pad, n, r.replace('.', '-')) for n, r in zip(names, rows))
+    pad = max([len(n) for n in names] + [len('#=GC RF')])
+    lines = ['# STOCKHOLM 1.0', '']
+    gs = ['#=GS %-*s DE %s' % (max(len(n) for n in names) if names else 1, n, d) for n, d in zip(names, descs) if d]
+    if gs:
+        lines += gs + ['']
+    for n, r in zip(names, rows):
+        lines.append('%-*s %s' % (pad, n, r))
+    lines.append('%-*s %s' % (pad, '#=GC RF', rf))
+    lines.append('//')
+    return '\n'.join(lines) + '\n'
 
 
 def write_domtblout(models, hits, bin_index, seq_base, names, descs, path):

@@ -151,6 +151,14 @@ int  ckm_search(ckm_engine *e, const ckm_models *m, const int32_t *model_idx, in
 int  ckm_search_per_bin(ckm_engine *e, const ckm_models *m, const int32_t *model_idx, const int64_t *bin_model_offsets,
                         const ckm_seqdb *db, double E, double domE, ckm_hit **hits_out, int64_t *nhits_out);
 void ckm_hits_free(ckm_hit *hits);
+
+/* ---- hmmalign: optimal-accuracy alignment of every sequence of `db` to ONE model, configured as `hmmalign` does (unihit
+ * local; Forward, Backward, posterior decoding, optimal-accuracy fill + traceback over the whole sequence).
+ * replaces HMMERRunner.align = os.system('hmmalign --outformat ... db query > out') (checkm/hmmer.py:76-95), whose output
+ * CheckM masks down to the match columns (checkm/hmmerAligner.py:276-358).
+ * state_out[r] for residue r of the unpadded stream (ckm_seqdb_create offsets): k > 0 emitted by match state k, k < 0 by
+ * insert state -k, 0 unaligned flank.  oasc_out[nseq] (optional): the optimal-accuracy score, 0 if no alignment exists. ---- */
+int  ckm_align(ckm_engine *e, const ckm_models *m, int32_t model, const ckm_seqdb *db, int32_t *state_out, float *oasc_out);
 int  ckm_last_stats(const ckm_engine *e, ckm_stats *out);
 
 /* stage-level entry points for parity tests (device arrays come back to host buffers the caller owns) */

@@ -1141,7 +1141,7 @@ enum { ST_M = 1, ST_D, ST_I, ST_S, ST_N, ST_B, ST_E, ST_C, ST_T, ST_J };
 
 /* OA traceback; we only need the first B..E segment: first/last M state. */
 static int oa_trace(const orc_profile *p, specials sp, const fmx *pp, const fmx *ox,
-                    int *hmmfrom, int *hmmto, int *sqfrom, int *sqto)
+                    int *hmmfrom, int *hmmto, int *sqfrom, int *sqto, int *trace /* optional, [L+1]: +k match, -k insert */)
 {
   int M = p->M, i = ox->L, k = 0, s0 = ST_C, s1;
   int firstM_i = 0, firstM_k = 0, lastM_i = 0, lastM_k = 0, have_last = 0, guard = 0;
@@ -1203,6 +1203,9 @@ static int oa_trace(const orc_profile *p, specials sp, const fmx *pp, const fmx 
     if (s1 == ST_M) {
       if (!have_last || s0 == ST_E) { lastM_i = i; lastM_k = k; have_last = 1; }
       firstM_i = i; firstM_k = k;
+      if (trace) trace[i] = k;
+    } else if (s1 == ST_I) {
+      if (trace) trace[i] = -k;
     }
     if ((s1 == ST_N || s1 == ST_J || s1 == ST_C) && s1 == s0) i--;
     s0 = s1;
@@ -1490,7 +1493,7 @@ static int rescore_isolated_domain(ddef_t *dd, const orc_profile *p, const uint8
   }
   oasc = optimal_accuracy(p, sp, ox2, ox1);
   int hf, ht, sf, st;
-  if (oa_trace(p, sp, ox2, ox1, &hf, &ht, &sf, &st)) { fmx_free(ox1); fmx_free(ox2); return 1; }
+  if (oa_trace(p, sp, ox2, ox1, &hf, &ht, &sf, &st, NULL)) { fmx_free(ox1); fmx_free(ox2); return 1; }
   float domcorrection = 0.0f;
   for (int pos = i; pos <= j; pos++) domcorrection += dd->n2sc[pos];
   if (dd->ndom == dd->dom_alloc) { dd->dom_alloc = dd->dom_alloc ? dd->dom_alloc * 2 : 4; dd->dcl = (orc_domain *)realloc(dd->dcl, sizeof(orc_domain) * dd->dom_alloc); }
@@ -1631,6 +1634,58 @@ int orc_pipeline(const orc_profile *p, const uint8_t *dsq, int L, orc_hit *hit)
   }
   free(dd.btot);
   return 1;
+}
+
+/* =====================================================================================
+ * hmmalign (checkm/hmmer.py:76-95 -> `hmmalign`): one sequence against one model, unihit local, the whole sequence as the
+ * envelope: Forward, Backward, posterior decoding, optimal-accuracy fill and traceback.  state[i-1] for residue i:
+ * +k = emitted by match state k, -k = by insert state k, 0 = unaligned flank (N / C).  Returns 0 on success.
+ * ===================================================================================== */
+/* optimal-accuracy trace of the envelope [i..j] of a sequence of length L (unihit, length model of the full sequence) */
+static int align_range(const orc_profile *p, const uint8_t *dsq, int L, int i, int j, int *state, float *ret_oasc)
+{
+  int Ld = j - i + 1;
+  specials sp = make_specials(L, 0);
+  fmx *ox1 = fmx_create(p->M, Ld, 1), *ox2 = fmx_create(p->M, Ld, 1);
+  float envsc;
+  forward_engine(p, dsq + i - 1, Ld, sp, ox1, &envsc);
+  backward_engine(p, dsq + i - 1, Ld, sp, ox1, ox2, NULL);
+  int rc = 1;
+  if (!decoding(sp, ox1, ox2)) {
+    float oasc = optimal_accuracy(p, sp, ox2, ox1);
+    int hf, ht, sf, st;
+    int *trace = (int *)calloc((size_t)Ld + 1, sizeof(int));
+    if (!oa_trace(p, sp, ox2, ox1, &hf, &ht, &sf, &st, trace)) {
+      for (int r = 1; r <= Ld; r++) state[i - 1 + r - 1] = trace[r];
+      if (ret_oasc) *ret_oasc = oasc;
+      rc = 0;
+    }
+    free(trace);
+  }
+  fmx_free(ox1); fmx_free(ox2);
+  return rc;
+}
+
+int orc_pipeline(const orc_profile *p, const uint8_t *dsq, int L, orc_hit *hit);
+
+int orc_align(const orc_profile *p, const uint8_t *dsq, int L, int *state, float *ret_oasc)
+{
+  for (int i = 0; i < L; i++) state[i] = 0;
+  if (ret_oasc) *ret_oasc = 0.0f;
+  if (L == 0) return 0;
+  if (align_range(p, dsq, L, 1, L, state, ret_oasc) == 0) return 0;
+  /* One unihit envelope cannot hold a sequence with a second strong copy of the domain (scaled fp32: the Backward pass overflows
+   * where the Forward pass has underflowed).  Such a sequence is aligned over the envelope of its best-scoring domain as the
+   * search pipeline defines it; the rest of it is flank. */
+  for (int i = 0; i < L; i++) state[i] = 0;
+  orc_hit hit;
+  if (!orc_pipeline(p, dsq, L, &hit)) return 1;
+  int best = -1;
+  for (int d = 0; d < hit.ndom; d++) if (best < 0 || hit.dcl[d].bitscore > hit.dcl[best].bitscore) best = d;
+  int rc = 1;
+  if (best >= 0) rc = align_range(p, dsq, L, hit.dcl[best].ienv, hit.dcl[best].jenv, state, ret_oasc);
+  free(hit.dcl);
+  return rc;
 }
 
 /* =====================================================================================

@@ -137,6 +137,9 @@ int   orc_filters(const orc_profile *p, const uint8_t *dsq, int L, orc_filter_re
 /* ---- full per-target pipeline; returns 1 and fills *hit if the target reaches the hit list ---- */
 int   orc_pipeline(const orc_profile *p, const uint8_t *dsq, int L, orc_hit *hit);
 
+/* ---- hmmalign: optimal-accuracy alignment of one sequence to one model (unihit local); state[i-1] = +k match / -k insert / 0 flank ---- */
+int   orc_align(const orc_profile *p, const uint8_t *dsq, int L, int *state, float *ret_oasc);
+
 /* ---- search: all models x all sequences, thresholds E<=Ecut, domE<=domEcut, Z=nseq ---- */
 typedef struct {
   int      nhits;

@@ -78,6 +78,7 @@ def lib():
         L.orc_striped_create.restype = C.c_void_p
         L.orc_striped_create.argtypes = [C.c_void_p]
         L.orc_striped_free.argtypes = [C.c_void_p]
+        L.orc_align.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_float)]
         L.orc_stage_scores.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int]
         _LIB = L
@@ -116,6 +117,7 @@ class HmmFile:
 
     def __init__(self, path):
         L = lib()
+        self.path = path
         self._h = C.c_void_p()
         n = C.c_int()
         st = L.orc_hmmfile_read(path.encode(), C.byref(self._h), C.byref(n))
@@ -170,6 +172,15 @@ def msv(hf, m, dsq):
 def ssv_xe(hf, m, dsq):
     d = np.ascontiguousarray(dsq, dtype=np.uint8)
     return lib().orc_ssv_xe(hf.prof_ptrs[m], d.ctypes.data, len(d))
+
+
+def align(hf, m, dsq):
+    """hmmalign of one sequence to model m: (state per residue: +k match / -k insert / 0 flank, optimal-accuracy score)."""
+    d = np.ascontiguousarray(dsq, dtype=np.uint8)
+    state = np.zeros(len(d), dtype=np.int32)
+    sc = C.c_float()
+    rc = lib().orc_align(hf.prof_ptrs[m], d.ctypes.data, len(d), state.ctypes.data, C.byref(sc))
+    return state, sc.value, rc
 
 
 def stage_scores(hf, residues, offsets, models=None, msv=True, vit=True, fwd=True, nthreads=1):
