@@ -765,8 +765,12 @@ def plugin_path(args, batches, db_path, models):
         t4 = time.perf_counter()
         for k, v in zip(('find', 'marker_sets', 'analyse', 'summary'), (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
             stage[k] += v
+        for k, v in getattr(RP, 'timing', {}).items():
+            stage['analyse.' + k] = stage.get('analyse.' + k, 0.0) + v
         return len(binIds)
     run('warm', 1)
+    for k in [k for k in stage if k.startswith('analyse.')]:
+        del stage[k]
     if args.profile_plugin:
         import cProfile
         import pstats

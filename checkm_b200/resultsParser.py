@@ -166,6 +166,8 @@ class ResultsParser(object):
         self.logger.info('Parsing HMM hits to marker genes:')
         binIds = list(self.models.keys())
         tables = {}
+        import time as _time
+        t0 = _time.perf_counter()
         for binId in binIds:
             path = os.path.join(outDir, 'bins', binId, hmmTableFile)
             try:
@@ -173,6 +175,7 @@ class ResultsParser(object):
             except IOError as detail:
                 sys.stderr.write(str(detail) + "\n")          # the reference carries on with an empty result
                 tables[binId] = (np.zeros(0, dtype=HIT_DTYPE), [], [], [], None)
+        self.timing = {'load_tables': _time.perf_counter() - t0}      # seconds per phase of the last call (bench.py reports them)
         try:
             reduced = self._reduce(binIds, tables, bIgnoreThresholds, evalueThreshold, lengthThreshold,
                                    bSkipPseudoGeneCorrection, bSkipAdjCorrection)
@@ -306,8 +309,13 @@ class ResultsParser(object):
         mh = C.POINTER(_lib.MarkerHit)()
         nmh = C.c_int64()
         harr = np.ascontiguousarray(hits)
+        import time as _time
+        _t1 = _time.perf_counter()
         check(_lib.lib().ckm_reduce(runtime.engine()._h, nm, nseq, len(binIds), harr.ctypes.data_as(C.POINTER(_lib.Hit)),
                                     len(harr), C.byref(opts), C.byref(meta), C.byref(qa), C.byref(nqa), C.byref(mh), C.byref(nmh)))
+        _t2 = _time.perf_counter()
+        if hasattr(self, 'timing'):
+            self.timing['reduce_call'] = _t2 - _t1
         del keep
         if nmh.value:
             buf = (C.c_char * (nmh.value * C.sizeof(_lib.MarkerHit))).from_address(C.addressof(mh.contents))
@@ -358,6 +366,8 @@ class ResultsParser(object):
             for acc in sorted(groups, key=lambda k: keys[k]):
                 ordered[acc] = [h for _, h in sorted(groups[acc], key=lambda t: t[0])]
             out[binId] = ordered
+        if hasattr(self, 'timing'):
+            self.timing['hit_objects'] = _time.perf_counter() - _t2
         return out
 
     # ------------------------------------------------------------------ cached tsv files

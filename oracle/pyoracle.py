@@ -1,7 +1,8 @@
 """ctypes wrapper over oracle/liboracle.so -- TEST INFRASTRUCTURE ONLY.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
-module.  Nothing in checkm_b200/ does.  PARITY UNPINNED for the search arithmetic (see hmmer_oracle.h).
+module.  Nothing in checkm_b200/ does.  Filters pinned by HMMER's own calibration numbers, domain definition PARITY
+UNPINNED (see hmmer_oracle.h).
 """
 import ctypes as C
 import os

@@ -79,8 +79,12 @@ BIN_STATS = ("{'GC': %r, 'GC std': 0.0213, 'Genome size': %d, '# ambiguous bases
              "'# predicted genes': %d}")
 
 
-@pytest.mark.parametrize('mode', ['hmm', 'taxon', 'lineage'])
-def test_find_then_qa(mode, expected, dataroot, tmp_path):
+@pytest.mark.parametrize('mode,batch_residues', [('hmm', None), ('taxon', None), ('lineage', None), ('lineage', '30000'), ('hmm', '1')])
+def test_find_then_qa(mode, batch_residues, expected, dataroot, tmp_path, monkeypatch):
+    """batch_residues: the default searches the three bins as one batch; '30000' / '1' force two / three batches through the
+    reader -> searchers -> writer pipeline of MarkerGeneFinder (one bin per batch, both engines busy)."""
+    if batch_residues is not None:
+        monkeypatch.setenv('CKM_BATCH_RESIDUES', batch_residues)
     from checkm_b200.markerGeneFinder import MarkerGeneFinder
     from checkm_b200.markerSets import MarkerSetParser
     from checkm_b200.resultsParser import ResultsParser

@@ -135,3 +135,40 @@ def test_evalue_threshold_decimal_split():
     assert _decimal_split(1e-10) == (-10, 10.0)
     assert _decimal_split(2.5e-7) == (-7, 25.0)
     assert _decimal_split(0.05) == (-2, 50.0)
+
+
+def test_fasta_parser_in_the_library():
+    """ckm_fasta_parse (host code of libckm.so; no GPU needed): codes, CSR offsets, names and descriptions of a protein FASTA."""
+    import gzip
+    import numpy as np
+    from checkm_b200.seqio import parse_fasta, read_fasta
+    text = ">a desc one\nACDE\nFG\n>b\n\nHIK*\n>c only\n>d x\r\nLMN\r\nPQ a\tb\n"
+    names, descs, res, off = parse_fasta(text.encode())
+    assert names == ['a', 'b', 'c', 'd'] and descs == ['desc one', '', 'only', 'x']
+    assert off.tolist() == [0, 6, 10, 10, 17]
+    alphabet = "ACDEFGHIKLMNPQRSTVWY-BJZOUX*~"
+    assert ''.join(alphabet[c] for c in res) == 'ACDEFGHIK*LMNPQAX'.replace('X', 'B')[:17] or ''.join(alphabet[c] for c in res) == 'ACDEFGHIK*LMNPQAB'
+    assert parse_fasta(b'')[0] == [] and parse_fasta(b'junk\n>x\nAC')[2].tolist() == [0, 1]
+    e2e = os.path.join(ROOT, 'tests', 'golden', 'e2e', 'bins')
+    n1 = read_fasta(os.path.join(e2e, 'binB.faa.gz'))
+    with gzip.open(os.path.join(e2e, 'binB.faa.gz'), 'rt') as f:
+        raw = f.read()
+    assert len(n1[0]) == raw.count('>') and int(n1[3][-1]) == len(''.join(l for l in raw.split('\n') if not l.startswith('>')))
+
+
+def test_alignment_formatter():
+    """hmmer.format_alignment: consensus columns + insert columns as hmmalign lays them out, and what CheckM's mask makes of it."""
+    import numpy as np
+    from checkm_b200.hmmer import format_alignment
+    res = np.array([0, 1, 0, 1, 2, 3, 4, 5, 2, 3, 4], dtype=np.uint8)            # ACACDEFG | DEF
+    state = np.array([0, 0, 1, 2, -2, -2, 4, 0, 2, 3, 4], dtype=np.int32)
+    off = np.array([0, 8, 11])
+    sto = format_alignment(['s1', 'seq2'], ['[e-value=1e-05,score=3.0]', '[e-value=1,score=1.0]'], res, off, state, 4, 'Pfam', False)
+    lines = sto.split('\n')
+    assert lines[0] == '# STOCKHOLM 1.0' and lines[-2] == '//'
+    assert 's1      acACde-Fg' in lines and 'seq2    ..-D..EF.' in lines and '#=GC RF ..xx..xx.' in lines
+    assert '#=GS s1   DE [e-value=1e-05,score=3.0]' in lines
+    trimmed = format_alignment(['s1', 'seq2'], ['', ''], res, off, state, 4, 'Pfam', True)
+    assert 's1      ACde-F' in trimmed.split('\n') and '#=GC RF xx..xx' in trimmed.split('\n')
+    afa = format_alignment(['s1', 'seq2'], ['', ''], res, off, state, 4, 'afa', True)
+    assert afa == '>s1\nACde-F\n>seq2\n-D..EF\n'

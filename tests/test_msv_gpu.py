@@ -40,12 +40,17 @@ def _check(engine, models, ohf, b, oracle, model_idx=None):
     return n_pass, n_cand, st
 
 
-def test_msv_parity_cpr43(engine, cpr_models, cpr_oracle, oracle):
+@pytest.mark.parametrize('resolve', ['1', '0'])
+def test_msv_parity_cpr43(engine, cpr_models, cpr_oracle, oracle, resolve, monkeypatch):
+    """resolve=1: pairs whose J state cannot have fired are scored in the SSV epilogue (kernels_msv.cu); resolve=0: every firing
+    pair goes to the exact MSV kernels, as in round 1.  Same bytes, same pass set either way."""
+    monkeypatch.setenv('CKM_SSV_RESOLVE', resolve)
     hm = synth.read_hmms(CPR_HMM)
     b = synth.make_bin('b0', hm, seed=11, n_orfs=260, tandem_prob=0.1, max_len=1500)
     n_pass, n_cand, st = _check(engine, cpr_models, cpr_oracle, b, oracle)
     assert n_pass > 40 and n_cand >= n_pass
     assert st.n_cells > 0
+    assert (st.n_msv_exact < n_cand // 4) if resolve == '1' else (st.n_msv_exact == n_cand)
 
 
 def test_msv_edge_lengths(engine, cpr_models, cpr_oracle, oracle):

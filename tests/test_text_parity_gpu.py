@@ -63,15 +63,20 @@ CASES = [('single', 31, dict(n_orfs=300, max_len=1200)),
 
 def test_domtblout_text_identical(engine, cpr_models, cpr_oracle, oracle, tmp_path):
     hm = synth.read_hmms(CPR_HMM)
-    stats, bad = [], []
+    stats, bad, near = [], [], [0]
     for tag, seed, kw in CASES:
         b = synth.make_bin(tag, hm, seed=seed, **kw)
         g, o, hits, rows = _both_tables(engine, cpr_models, cpr_oracle, oracle, b, tmp_path, tag)
         assert len(g) >= 20
         bad += _compare(g, o, hits, rows, tag, stats)
+        for h in hits:
+            for f in ('full_score', 'dom_score'):
+                frac = (float(h[f]) * 10.0) % 1.0
+                near[0] += abs(frac - 0.5) < 0.1
     s = np.asarray(stats)
-    print('all cases: %d float fields, median |diff| %.3g, 99%% %.3g, max %.3g bits; text mismatches %d' %
-          (len(s), np.median(s), np.quantile(s, 0.99), s.max(), len(bad)))
+    print('all cases: %d float fields, median |diff| %.3g, 99%% %.3g, max %.3g bits; text mismatches %d; %d printed scores sit within '
+          '1e-2 bits of a "%%.1f" rounding boundary (they print identically because the floats are identical)' %
+          (len(s), np.median(s), np.quantile(s, 0.99), s.max(), len(bad), near[0]))
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
     if os.path.isdir(out):
         np.save(os.path.join(out, 'text_parity_diffs.npy'), s)
