@@ -47,31 +47,6 @@ class MarkerHit(object):
         return "\t".join(str(getattr(self, f)) for f in self.__slots__)
 
 
-def _hit_from_row(row, name, desc, qname, qacc):
-    h = MarkerHit()
-    h.target_name = name
-    h.target_accession = '-'
-    h.target_length = int(row['tlen'])
-    h.query_name = qname
-    h.query_accession = qacc
-    h.query_length = int(row['qlen'])
-    h.full_e_value = float('%9.2g' % row['full_evalue'])
-    h.full_score = float('%6.1f' % row['full_score'])
-    h.full_bias = float('%5.1f' % row['full_bias'])
-    h.dom = int(row['dom'])
-    h.ndom = int(row['ndom'])
-    h.c_evalue = float('%9.2g' % row['c_evalue'])
-    h.i_evalue = float('%9.2g' % row['i_evalue'])
-    h.dom_score = float('%6.1f' % row['dom_score'])
-    h.dom_bias = float('%5.1f' % row['dom_bias'])
-    h.hmm_from, h.hmm_to = int(row['hmm_from']), int(row['hmm_to'])
-    h.ali_from, h.ali_to = int(row['ali_from']), int(row['ali_to'])
-    h.env_from, h.env_to = int(row['env_from']), int(row['env_to'])
-    h.acc = float('%4.2f' % row['acc'])
-    h.target_description = desc
-    return h
-
-
 def _decimal_split(x):
     """x = mant * 10^(exp10-1) with 10 <= mant < 100, from the shortest decimal text of x (exact for 1e-10 etc.)."""
     if x <= 0:
@@ -324,11 +299,19 @@ class ResultsParser(object):
             marker_hits = np.zeros(0, dtype=MH_DTYPE)
         _lib.lib().ckm_free(qa)
         _lib.lib().ckm_free(mh)
-        # back to {binId: {acc: [hits]}} in the reference's dict order: non-Pfam markers in file order, then Pfam markers
+        # back to {binId: {acc: [hits]}} in the reference's dict order: non-Pfam markers in file order, then Pfam markers.
+        # Columns are pulled out of the record arrays once (plain Python lists): indexing numpy records hit by hit is what
+        # this loop would otherwise spend its time on.
         out = {}
+        mh = {f: marker_hits[f].tolist() for f in ('bin', 'model', 'seq_a', 'seq_b', 'target_length', 'hmm_from', 'hmm_to', 'ali_from',
+                                                   'ali_to', 'env_from', 'env_to', 'order', 'src_row', 'dict_key')}
+        src_rows = harr[marker_hits['src_row']] if len(marker_hits) else harr[:0]
+        sc = {f: src_rows[f].tolist() for f in ('seq', 'tlen', 'qlen', 'dom', 'ndom', 'full_score', 'full_bias', 'dom_score', 'dom_bias', 'acc',
+                                                'full_evalue', 'c_evalue', 'i_evalue')}
         per_bin = defaultdict(list)
-        for rec in marker_hits:
-            per_bin[int(rec['bin'])].append(rec)
+        for z, bb in enumerate(mh['bin']):
+            per_bin[bb].append(z)
+        concat = DefaultValues.SEQ_CONCAT_CHAR
         for b, binId in enumerate(binIds):
             rows, names, descs, qids, _parsed = tables[binId]
             base = bases[binId]
@@ -336,32 +319,43 @@ class ResultsParser(object):
             for qn, qa_ in qids:
                 qname_of.setdefault(qa_ if qa_ not in ('-', '') else qn, qn)
             groups, keys = {}, {}
-            for pos, rec in enumerate(per_bin.get(b, [])):
-                acc = accs[int(rec['model'])]
-                if acc not in groups:
-                    groups[acc] = []
-                    dk = int(rec['dict_key'])
+            for pos, z in enumerate(per_bin.get(b, ())):
+                acc = accs[mh['model'][z]]
+                lst = groups.get(acc)
+                if lst is None:
+                    lst = groups[acc] = []
+                    dk = mh['dict_key'][z]
                     keys[acc] = (0, pos) if dk < 0 else (1, dk)
-                src = harr[int(rec['src_row'])]
-                a = int(rec['seq_a']) - base
-                qname = qname_of.get(acc)
-                original = parsed_all[int(rec['src_row'])]
+                original = parsed_all[mh['src_row'][z]]
+                hit = MarkerHit()
                 if original is not None:
-                    hit = MarkerHit()
                     for f in MarkerHit.__slots__:
                         setattr(hit, f, getattr(original, f))
                 else:
-                    hit = _hit_from_row(src, names[int(src['seq']) - base], descs[int(src['seq']) - base] if descs else '',
-                                        qname if qname is not None else acc, acc)
-                if rec['seq_b'] >= 0:
-                    bname = names[int(rec['seq_b']) - base]
+                    si = sc['seq'][z] - base
+                    hit.target_name = names[si]
+                    hit.target_accession = '-'
+                    hit.query_name = qname_of.get(acc, acc)
+                    hit.query_accession = acc
+                    hit.query_length = sc['qlen'][z]
+                    hit.full_e_value = float('%9.2g' % sc['full_evalue'][z])
+                    hit.full_score = float('%6.1f' % sc['full_score'][z])
+                    hit.full_bias = float('%5.1f' % sc['full_bias'][z])
+                    hit.dom, hit.ndom = sc['dom'][z], sc['ndom'][z]
+                    hit.c_evalue = float('%9.2g' % sc['c_evalue'][z])
+                    hit.i_evalue = float('%9.2g' % sc['i_evalue'][z])
+                    hit.dom_score = float('%6.1f' % sc['dom_score'][z])
+                    hit.dom_bias = float('%5.1f' % sc['dom_bias'][z])
+                    hit.acc = float('%4.2f' % sc['acc'][z])
+                    hit.target_description = descs[si] if descs else ''
+                if mh['seq_b'][z] >= 0:
                     # the merged object is hits[i] mutated (resultsParser.py:451-470): scores and description stay
-                    hit.target_name = DefaultValues.SEQ_CONCAT_CHAR.join([names[a], bname])
-                hit.target_length = int(rec['target_length'])
-                hit.hmm_from, hit.hmm_to = int(rec['hmm_from']), int(rec['hmm_to'])
-                hit.ali_from, hit.ali_to = int(rec['ali_from']), int(rec['ali_to'])
-                hit.env_from, hit.env_to = int(rec['env_from']), int(rec['env_to'])
-                groups[acc].append((int(rec['order']), hit))
+                    hit.target_name = concat.join([names[mh['seq_a'][z] - base], names[mh['seq_b'][z] - base]])
+                hit.target_length = mh['target_length'][z]
+                hit.hmm_from, hit.hmm_to = mh['hmm_from'][z], mh['hmm_to'][z]
+                hit.ali_from, hit.ali_to = mh['ali_from'][z], mh['ali_to'][z]
+                hit.env_from, hit.env_to = mh['env_from'][z], mh['env_to'][z]
+                lst.append((mh['order'][z], hit))
             ordered = {}
             for acc in sorted(groups, key=lambda k: keys[k]):
                 ordered[acc] = [h for _, h in sorted(groups[acc], key=lambda t: t[0])]
