@@ -8,7 +8,6 @@ SURVEY.md section 8) with ckm_align; `press` has nothing to do.
 
 `HMMERParser` / `HmmerHitDOM` / `HmmerHitTBL` read the tabular text back exactly like hmmer.py:140-311."""
 import logging
-import os
 import re
 import sys
 

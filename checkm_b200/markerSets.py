@@ -4,7 +4,6 @@ in-memory model database instead of `hmmfetch -f` + `hmmfetch --index` subproces
 File formats, selection rules and the exclusion list are the reference's; completeness/contamination arithmetic
 (`MarkerSet.genomeCheck`, markerSets.py:206-238) is kept here as the host-side statement of what the device
 reduction computes (ckm_reduce R4), summed in the same list order."""
-import ast
 import gzip
 import logging
 import os

@@ -135,3 +135,27 @@ def test_queue_overflow_is_retried(engine, cpr_models, cpr_oracle, oracle):
     got = sorted((int(h['model']), int(h['seq']), int(h['hmm_from']), int(h['hmm_to']), int(h['ali_from']), int(h['ali_to'])) for h in hits if h['seq'] < 200)
     want = sorted((idx[r['model']], r['seqidx'], r['hmm_from'], r['hmm_to'], r['ali_from'], r['ali_to']) for r in rows)
     assert got == want and len(want) >= 600
+
+
+def test_search_wide_classes_and_long_models(engine, oracle, tmp_path):
+    """Lane-block classes the fixture's models do not reach (Q = 24: M = 700, Q = 32: M = 1000): bit-exact like the rest.
+    M = 1100 and 2500 have no blocked class (chunked kernels; M = 2500 is a chained SSV tile): coordinates exact, scores within the
+    stated tolerance."""
+    p = str(tmp_path / 'wide.hmm')
+    ms = synth.make_model_db(p, CPR_HMM, [700, 1000, 1100, 2500], seed=21)
+    ohf = oracle.HmmFile(p)
+    models = engine.load_models(p)
+    b = synth.make_bin('w', ms, seed=22, n_orfs=40, copies=(1, 2), max_len=3000, split_prob=0.0, tandem_prob=0.2)
+    db = engine.seqdb(b.residues, b.offsets)
+    hits = engine.search(models, db)
+    db.close()
+    rp = oracle.search(ohf, b.residues, b.offsets, nthreads=8)
+    rows = oracle.hits_table(rp)
+    oracle.free_results(rp)
+    assert len(rows) == len(hits) and len(rows) >= 6
+    blocked = [(r, h) for r, h in zip(rows, hits) if r['model'] < 2]
+    chunked = [(r, h) for r, h in zip(rows, hits) if r['model'] >= 2]
+    assert blocked and chunked
+    compare([r for r, _ in blocked], np.array([h for _, h in blocked], dtype=hits.dtype), exact=True)
+    compare([r for r, _ in chunked], np.array([h for _, h in chunked], dtype=hits.dtype), exact=False)
+    models.close()
