@@ -125,6 +125,20 @@ def test_oracle_reproduces_hmmer_calibration(cpr_oracle, oracle):
     print('43 models: worst |mu_MSV| %.2g, |mu_VIT| %.2g, |tau_FWD| %.2g bits against the STATS lines' % tuple(worst))
 
 
+def test_lambda_of_the_stats_lines(cpr_oracle):
+    """hmmbuild sets the slope of all three score distributions analytically, lambda = ln 2 + 1.44 / (M x H) with H the mean
+    relative entropy per match state against the background (bits): the oracle's parsed emission probabilities and background
+    frequencies reproduce the lambda printed in every STATS line (5 decimals)."""
+    for m in range(cpr_oracle.n):
+        h = cpr_oracle.headers[m]
+        M = h.M
+        mat = np.ctypeslib.as_array(h.mat, shape=((M + 1) * 20,)).reshape(M + 1, 20)[1:].astype(np.float64)
+        q = _BGF.astype(np.float64)
+        H = sum(float((p[p > 0] * np.log2(p[p > 0] / q[p > 0])).sum()) for p in mat) / M
+        lam = np.log(2.0) + 1.44 / (M * H)
+        assert abs(lam - float(h.evparam[1])) < 1e-5 and h.evparam[1] == h.evparam[3] == h.evparam[5], (m, lam, list(h.evparam))
+
+
 def test_null_pass_rates(cpr_oracle, oracle):
     """Fresh i.i.d. sequences: the fractions passing P <= F1 (MSV) and P <= F2 (Viterbi) are the nominal ones to within
     the sampling error of the calibration itself (mu estimated from 200 samples: +-0.1 bits, i.e. +-7% in P)."""

@@ -1,4 +1,5 @@
 #!/bin/bash
+# round-end check on one B200: GPU tests, smoke, default bench + reference arm, launch list of the default command, configs 4 / 2, diverse db
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 ( time python -m pytest tests -m gpu -q ) > gpurun_out/r2_t9.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2_t9.log
