@@ -68,7 +68,7 @@ SYMBOLS = ["ckm_init", "ckm_destroy", "ckm_last_error", "ckm_version", "ckm_devi
            "ckm_models_write", "ckm_models_free", "ckm_digitize", "ckm_fasta_parse", "ckm_seqdb_create", "ckm_seqdb_free",
            "ckm_search", "ckm_search_per_bin", "ckm_hits_free", "ckm_align", "ckm_last_stats", "ckm_msv_scores",
            "ckm_filter_scores", "ckm_viterbi_scores", "ckm_write_domtblout", "ckm_reduce", "ckm_genome_check", "ckm_free", "ckm_allgather_qa", "ckm_nccl_unique_id",
-           "ckm_nccl_comm_init", "ckm_nccl_comm_destroy"]
+           "ckm_nccl_comm_init", "ckm_nccl_comm_destroy", "ckm_fasta_scan_nt", "ckm_scaffold_stats"]
 
 _lib = None
 
@@ -98,6 +98,8 @@ def lib():
     L.ckm_models_free.restype = None
     L.ckm_digitize.argtypes = [C.c_char_p, i64, vp]
     L.ckm_fasta_parse.argtypes = [C.c_char_p, i64, vp, vp, i32, vp, i64, C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]
+    L.ckm_fasta_scan_nt.argtypes = [C.c_char_p, i64, vp, i64, vp, vp, i32, vp, i64, C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]
+    L.ckm_scaffold_stats.argtypes = [vp, vp, i64, vp, vp, i32, vp, vp, vp, i64, C.POINTER(i64), C.POINTER(C.c_float)]
     L.ckm_seqdb_create.argtypes = [vp, vp, vp, i32, vp, i32, C.POINTER(vp)]
     L.ckm_seqdb_free.argtypes = [vp]
     L.ckm_seqdb_free.restype = None

@@ -163,6 +163,28 @@ class Engine:
         check(_lib.lib().ckm_align(self._h, models._h, int(model), db._h, state.ctypes.data, oasc.ctypes.data))
         return state, oasc
 
+    def scaffold_stats(self, data, starts, lens):
+        """Base counts and contigs of scaffolds laid out as `seqio.scan_nt_fasta` returns them (ckm_scaffold_stats).
+        Returns stats (n x 8 int64: A C G T 'N' 'n' contigs contig-bases), the scaffold index and length of every contig
+        (no particular order), and the scan kernel's duration in ms."""
+        n = len(lens)
+        stats = np.zeros((n, 8), dtype=np.int64)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        starts = np.ascontiguousarray(starts, dtype=np.int64)
+        lens = np.ascontiguousarray(lens, dtype=np.int64)
+        cap = n + int(lens.sum()) // 2048 + 1024
+        while True:
+            cscaf = np.empty(cap, dtype=np.uint32)
+            clen = np.empty(cap, dtype=np.uint32)
+            found, ms = C.c_int64(), C.c_float()
+            rc = _lib.lib().ckm_scaffold_stats(self._h, data.ctypes.data, data.size, starts.ctypes.data, lens.ctypes.data, n,
+                                               stats.ctypes.data, cscaf.ctypes.data, clen.ctypes.data, cap, C.byref(found), C.byref(ms))
+            if rc == 8 and found.value > cap:          # CKM_ECAPACITY: the count needed came back
+                cap = found.value
+                continue
+            check(rc)
+            return stats, cscaf[:found.value].astype(np.int64), clen[:found.value].astype(np.int64), float(ms.value)
+
     def close(self):
         if self._h:
             _lib.lib().ckm_destroy(self._h)

@@ -245,6 +245,25 @@ void ckm_nccl_comm_destroy(void *comm);
 int  ckm_allgather_qa(ckm_engine *e, void *nccl_comm, const ckm_qa_row *rows, int32_t nrows, int32_t nrows_max,
                       int32_t world, ckm_qa_row *rows_out, int32_t *counts_out);
 
+/* ---- bin statistics (checkm/binStatistics.py:99-139,176-243): the integer half -- base counts,
+ * ambiguous bases and the contig lengths of every scaffold -- as one byte scan on the device; the caller forms GC, N50 and
+ * the means from these integers exactly as the reference does from its own counts. ---- */
+/* a nucleotide FASTA file read the way checkm/util/seqUtils.py:180-211 readFasta reads it (text-mode line ends, blank lines
+ * skipped, the last character of a final unterminated line lost).  Record r occupies bytes_out[starts_out[r] ..
+ * starts_out[r] + lens_out[r]), starts are multiples of 64 and the gaps are zero: the layout ckm_scaffold_stats wants.
+ * bytes_cap >= n + 64 * (max_records + 1) always suffices.  Header lines come back as in ckm_fasta_parse. */
+int  ckm_fasta_scan_nt(const char *text, int64_t n, uint8_t *bytes_out, int64_t bytes_cap, int64_t *starts_out, int64_t *lens_out,
+                       int32_t max_records, char *headers_out, int64_t headers_cap, int32_t *nrec_out, int64_t *bytes_used_out,
+                       int64_t *hdr_bytes_out);
+/* stats_out: nscaf x 8 int64 = {A, C, G, T+U (all case-insensitive, seqUtils.py:279-286), 'N', 'n', contigs, contig bases};
+ * a contig is a stretch between runs of >= 10 'N' (DefaultValues.CONTIG_BREAK), its length the bytes in it that are not 'N'
+ * (binStatistics.py:208-226).  The contigs of all scaffolds come back as (scaffold, length) pairs in no particular order;
+ * with more than contig_cap of them the call fails with CKM_ECAPACITY and *ncontigs_out holds the number needed.
+ * kernel_ms_out (optional): duration of the scan kernel by CUDA events. */
+int  ckm_scaffold_stats(ckm_engine *e, const uint8_t *bytes, int64_t nbytes, const int64_t *starts, const int64_t *lens,
+                        int32_t nscaf, int64_t *stats_out, uint32_t *contig_scaffold_out, uint32_t *contig_len_out,
+                        int64_t contig_cap, int64_t *ncontigs_out, float *kernel_ms_out);
+
 #ifdef __cplusplus
 }
 #endif

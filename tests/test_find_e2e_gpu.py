@@ -208,3 +208,28 @@ def test_subsets_and_fetch(expected, dataroot, tmp_path, oracle):
     HMMERRunner(mode='fetch').fetch(DefaultValues.HMM_MODELS, 'TIGR00422', outp)
     assert oracle.HmmFile(outp).accs() == ['TIGR00422']
     assert runtime.models_for(DefaultValues.HMM_MODELS).n == 43
+
+
+def test_find_with_an_empty_gene_file(dataroot, tmp_path):
+    """A bin whose gene file is empty (no ORFs called) goes through find and qa like any other: empty table, zero counts
+    (the reference's "processing empty gene files" case)."""
+    from checkm_b200.markerGeneFinder import MarkerGeneFinder
+    from checkm_b200.markerSets import MarkerSetParser
+    from checkm_b200.resultsParser import ResultsParser
+    empty = tmp_path / 'nothing.faa'
+    empty.write_text('')
+    out = str(tmp_path / 'out')
+    os.makedirs(os.path.join(out, 'storage'))
+    for files in ([str(empty)], [str(empty), BINFILES[0]]):
+        models = MarkerGeneFinder(1).find(files, out, 'hmmer.analyze.txt', 'hmmer.analyze.ali.txt', CPR_HMM, False, False, True)
+        ids = ['nothing'] + (['binA'] if len(files) == 2 else [])
+        assert sorted(models.keys()) == sorted(ids)
+        assert _data_lines(os.path.join(out, 'bins', 'nothing', 'hmmer.analyze.txt')) == []
+        with open(os.path.join(out, 'storage', 'bin_stats.analyze.tsv'), 'w') as f:
+            for b in ids:
+                f.write("%s\t{'GC': 0.5}\n" % b)
+        RP = ResultsParser(models)
+        RP.analyseResults(out, 'bin_stats.analyze.tsv', 'hmmer.analyze.txt')
+        ms = MarkerSetParser(1).getMarkerSets(out, ids, CPR_HMM)
+        assert RP.results['nothing'].markerHits == {}
+        assert RP.results['nothing'].geneCountsForSelectedMarkerSet(ms['nothing'], False) == [43, 0, 0, 0, 0, 0, 0.0, 0.0]
