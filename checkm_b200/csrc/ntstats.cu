@@ -1,6 +1,6 @@
 // ntstats.cu -- base composition and contig structure of a bin's scaffolds: the integer half of CheckM's bin statistics
 // (checkm/binStatistics.py:176-243: calculateGC, calculateSeqStats).  Everything here is a byte scan
-// bound by HBM: a CTA walks a 128 KB segment of a scaffold in 16 KB tiles, a thread takes 64 consecutive bytes.
+// bound by HBM: 2 KB rows stream through shared memory by TMA bulk copies, one warp per row, a lane takes 64 consecutive bytes.
 //
 // What the reference computes per scaffold, restated as local predicates:
 //   * a, c, g, t: case-insensitive counts, U counted with T (util/seqUtils.py:279-286)
@@ -17,33 +17,36 @@
 #include <vector>
 #include "engine.hpp"
 #include "pool.hpp"
+#include "device_utils.cuh"
 
 using namespace ckm;
 
 namespace {
 
 constexpr int NT_THREADS = 256;
-constexpr int NT_CHUNK = 64;                         // bytes of one thread in one tile: one bit each in a 64-bit mask
-constexpr int NT_TILE = NT_THREADS * NT_CHUNK;       // 16 KB
-constexpr int NT_SEG_TILES = 8;
-constexpr int64_t NT_SEG = (int64_t)NT_TILE * NT_SEG_TILES;   // 128 KB: the unit of work of a CTA
-constexpr int NT_MAXSEG = NT_TILE / 11 + 8;          // run ends are >= 11 bytes apart
 constexpr int NT_WARPS = NT_THREADS / 32;
+constexpr int NT_CHUNK = 64;                         // bytes of one lane in one row: one bit each in a 64-bit mask
+constexpr int NT_ROW = 32 * NT_CHUNK;                // 2 KB: what a warp takes at a time
+constexpr int NT_HALO = 16;                          // bytes staged either side of a row (9 before and 1 after are looked at)
+constexpr int NT_STAGE = NT_HALO + NT_ROW + NT_HALO;
+constexpr int NT_STAGES = 3;                         // rows in flight per warp
+constexpr int NT_CTAS_PER_SM = 4;                    // 32 warps x 3 x 2 KB of stages = 195 KB of shared memory, <= 64 registers
 
-// A scaffold longer than NT_SEG is cut into segments scanned by different CTAs.  Contigs closed inside a segment are
-// reported by the kernel; of each segment the bases before its first run end (head) and after its last (tail) come back
-// separately and the host joins tail + head across the cuts (join_segments below).
-struct NtSegment { uint32_t head, tail, closed; };   // closed: the segment holds at least one run end
+// The scaffolds of a call, cut into 2 KB rows, form one list; every warp of the grid takes a contiguous range of it and
+// streams its rows through its own ring of shared-memory stages, filled by TMA bulk copies that lane 0 issues NT_STAGES
+// ahead.  Warps never wait for each other.  A "piece" is the part of one scaffold inside one warp's range.  Contigs closed
+// inside a piece are reported by the kernel; the bases before the first run end of a piece (head) and after its last (tail)
+// come back separately and the host joins tail + head across the cuts (ckm_scaffold_stats below).
+// Piece index = scaffold + warp: along the list one of the two grows at every cut.
+struct NtRow { int64_t src; uint32_t scaf; uint32_t info; };       // info: valid bytes (1..2048) | first row << 30 | last row << 31
+struct NtPiece { uint32_t head, tail, closed, pad; };              // closed: the piece holds at least one run end
 
 struct NtParams {
   const uint8_t *bytes;            // every scaffold starts at a multiple of 64 and is followed by padding up to the next one
-  const int64_t *starts, *lens;
-  const int32_t *seg_scaf;         // segments in scaffold order
-  const int64_t *seg_off;          // first byte of the segment inside its scaffold (a multiple of NT_SEG)
-  int32_t nseg;
-  int32_t *work;                   // next segment
-  NtSegment *seg;
-  unsigned long long *stats;       // nscaf x 8: a c g t N n contigs contig_bases (the last two: contigs closed inside segments)
+  const NtRow *rows;
+  long long nrows;
+  NtPiece *piece;                  // nscaf + warps of the grid, zeroed
+  unsigned long long *stats;       // nscaf x 8: a c g t N n contigs contig_bases (the last two: contigs closed inside pieces)
   uint32_t *contig_scaf, *contig_len;
   unsigned long long *ncontigs;
   long long cap;
@@ -57,162 +60,179 @@ __device__ __forceinline__ uint32_t eq4(uint32_t w, uint32_t pat) {
 }
 // the four 0x80 flags of eq4 as a 4-bit mask, byte 0 -> bit 0
 __device__ __forceinline__ uint32_t nibble(uint32_t flags) { return (((flags >> 7) * 0x01020408u) >> 24) & 0xFu; }
-// sum of the four bytes of x (each below 64)
+// sum of the four bytes of x (the sum must stay below 256)
 __device__ __forceinline__ uint32_t hsum4(uint32_t x) { return (x * 0x01010101u) >> 24; }
 
-__global__ void __launch_bounds__(NT_THREADS, 4) ntstats_kernel(NtParams p) {
-  __shared__ unsigned long long s_m[NT_THREADS];
-  __shared__ uint32_t s_acc[NT_MAXSEG];
-  __shared__ uint32_t s_wsum[NT_WARPS];
-  __shared__ unsigned long long s_tot[8];
-  __shared__ int s_next;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < NT_MAXSEG; i += NT_THREADS) s_acc[i] = 0;
-  if (tid < 8) s_tot[tid] = 0;
-  __syncthreads();
-  for (;;) {
-    if (tid == 0) s_next = atomicAdd(p.work, 1);
-    __syncthreads();
-    const int item = s_next;
-    if (item >= p.nseg) return;
-    const int s = p.seg_scaf[item];
-    const int64_t L = p.lens[s];
-    const int64_t seg_begin = p.seg_off[item];
-    const int64_t seg_end = min(L, seg_begin + NT_SEG);
-    const uint8_t *base = p.bytes + p.starts[s];
-    uint32_t cA = 0, cC = 0, cG = 0, cT = 0, cN = 0, cn = 0;     // per-thread counts over the segment
-    uint32_t carry = 0;                                          // bases of the contig still open (same in every thread)
-    uint32_t head = 0; bool closed = false;                      // same in every thread
-    uint32_t my_ctg = 0; unsigned long long my_ctg_bases = 0;
-    for (int64_t t0 = seg_begin; t0 < seg_end; t0 += NT_TILE) {
-      const int64_t pos = t0 + (int64_t)tid * NT_CHUNK;
-      unsigned long long m = 0, valid = 0;
-      if (pos < L) {
-        const int64_t left = L - pos;
-        valid = left >= NT_CHUNK ? ~0ull : ((1ull << left) - 1ull);
-        const uint4 *src = reinterpret_cast<const uint4 *>(base + pos);
-        uint32_t w[16];
+__device__ __forceinline__ void nt_issue(const NtParams &p, const NtRow d, uint32_t stage, NtRow *desc, uint64_t *bar) {
+  *desc = d;
+  const uint32_t nbytes = d.info & 0xFFFFu;
+  const uint32_t left = (d.info >> 30) & 1u ? 0u : (uint32_t)NT_HALO, right = (d.info >> 31) ? 0u : (uint32_t)NT_HALO;
+  const uint32_t bytes = left + (nbytes + 63u) / 64u * 64u + right;
+  fence_proxy_async();                                    // the stage was read through the generic proxy a moment ago
+  mbar_expect_tx(bar, bytes);
+  bulk_g2s(stage + NT_HALO - left, p.bytes + d.src - left, bytes, bar);
+}
+
+__device__ __forceinline__ void nt_emit(const NtParams &p, uint32_t scaf, uint32_t len) {
+  if (len == 0) return;
+  const unsigned long long at = atomicAdd(p.ncontigs, 1ull);
+  if ((long long)at < p.cap) { p.contig_scaf[at] = scaf; p.contig_len[at] = len; }
+  atomicAdd(&p.stats[(size_t)scaf * 8 + 6], 1ull);
+  atomicAdd(&p.stats[(size_t)scaf * 8 + 7], (unsigned long long)len);
+}
+
+__global__ void __launch_bounds__(NT_THREADS, NT_CTAS_PER_SM) ntstats_kernel(NtParams p) {
+  extern __shared__ __align__(128) uint8_t s_stage[];           // NT_WARPS x NT_STAGES x NT_STAGE
+  __shared__ __align__(16) NtRow s_desc[NT_WARPS][NT_STAGES];
+  __shared__ __align__(8) uint64_t s_bar[NT_WARPS][NT_STAGES];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * NT_WARPS + warp, nw = (long long)gridDim.x * NT_WARPS;
+  const long long lo = p.nrows * gw / nw, hi = p.nrows * (gw + 1) / nw;
+  if (lo >= hi) return;
+  const uint32_t ring = smem_u32(s_stage) + warp * (NT_STAGES * NT_STAGE);
+  NtRow upcoming = {0, 0u, 0u};                                  // lane 0: the row to issue next, fetched one row early
+  if (lane == 0) {
+    for (int i = 0; i < NT_STAGES; ++i) mbar_init(&s_bar[warp][i], 1);
+    fence_mbar_init();
+    for (int i = 0; i < NT_STAGES && lo + i < hi; ++i) nt_issue(p, p.rows[lo + i], ring + i * NT_STAGE, &s_desc[warp][i], &s_bar[warp][i]);
+    if (lo + NT_STAGES < hi) upcoming = p.rows[lo + NT_STAGES];
+  }
+  __syncwarp();
+  const int rot = (lane >> 1) & 3;                               // the lane reads its four 16-byte vectors starting at this one:
+                                                                 // eight neighbouring lanes then touch eight different bank groups
+  uint32_t cA = 0, cC = 0, cG = 0, cT = 0, cN = 0, cn = 0;       // per-lane counts over the piece
+  uint32_t carry = 0;                                            // bases of the contig still open (same in every lane)
+  uint32_t head = 0; bool closed = false;                        // same in every lane
+  int st = 0; uint32_t phase = 0;
+  for (long long k = lo; k < hi; ++k) {
+    mbar_wait(&s_bar[warp][st], phase);
+    const NtRow d = s_desc[warp][st];
+    const uint32_t s = d.scaf;
+    const int nbytes = (int)(d.info & 0xFFFFu);
+    const bool first_row = (d.info >> 30) & 1u, last_row = (d.info >> 31) != 0;
+    const uint32_t body = ring + st * NT_STAGE + NT_HALO;
+    const int left = nbytes - lane * NT_CHUNK;                   // bytes of the scaffold in and after this lane's chunk
+    uint32_t w[16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const uint4 v = __ldg(src + q); w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w; }
-        // Fast path, a chunk of nothing but upper-case A C G T (what assemblies mostly are): the low three bits of the
-        // four letters differ (A 1, C 3, T 4, G 7), so one byte permute looks up the letter each byte would have to be and
-        // one xor tells whether it is; then bits 1 and 2 of the byte give the letter: A 00, C 01, T 10, G 11.
-        uint32_t bad = left >= NT_CHUNK ? 0u : 1u;
-        uint32_t s1 = 0, s2 = 0, sg = 0;                         // per-byte sums over the 16 words: bit1, bit2, bit1 & bit2
+    for (int q = 0; q < 4; ++q) {
+      const uint4 v = lds128(body + lane * NT_CHUNK + ((q + rot) & 3) * 16);
+      w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+    }
+    // the two halo bytes groups, read before the stage is handed back: is-N of the 12 bytes before the row, of the byte after
+    uint32_t halo_bits = 0;
+    if (lane == 0 && !first_row) {
+      const uint4 v = lds128(body - NT_HALO);
+      halo_bits = nibble(eq4(v.y, 0x4E4E4E4Eu)) | (nibble(eq4(v.z, 0x4E4E4E4Eu)) << 4) | (nibble(eq4(v.w, 0x4E4E4E4Eu)) << 8);
+    }
+    if (lane == 31 && !last_row) halo_bits = s_stage[warp * (NT_STAGES * NT_STAGE) + st * NT_STAGE + NT_HALO + NT_ROW] == 'N';
+    __syncwarp();
+    // every lane holds its bytes in registers: the stage can take the row NT_STAGES further on
+    if (lane == 0 && k + NT_STAGES < hi) {
+      nt_issue(p, upcoming, ring + st * NT_STAGE, &s_desc[warp][st], &s_bar[warp][st]);
+      if (k + NT_STAGES + 1 < hi) upcoming = p.rows[k + NT_STAGES + 1];
+    }
+    if (++st == NT_STAGES) { st = 0; phase ^= 1u; }
+
+    unsigned long long m = 0, valid = 0;
+    if (left > 0) {
+      valid = left >= NT_CHUNK ? ~0ull : ((1ull << left) - 1ull);
+      // Fast path, a chunk of nothing but upper-case A C G T (what assemblies mostly are): the low three bits of the
+      // four letters differ (A 1, C 3, T 4, G 7), so one byte permute looks up the letter each byte would have to be and
+      // one xor tells whether it is.  Then bit 1 is set in C and G, bit 2 in G and T, bit 4 in T only.
+      uint32_t bad = left >= NT_CHUNK ? 0u : 1u;
+      uint32_t s1 = 0, s2 = 0, s4a = 0, s4b = 0;               // per-byte sums over the words of 2 x bit1, 4 x bit2, 16 x bit4 (two halves)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        uint32_t t = w[j] & 0x07070707u;
+        t |= t >> 4;
+        const uint32_t sel = __byte_perm(t, 0u, 0x4420);       // the four 3-bit indices as selector nibbles
+        const uint32_t expect = __byte_perm(0x43FF41FFu, 0x47FFFF54u, sel);
+        bad |= w[j] ^ expect;
+        s1 += w[j] & 0x02020202u; s2 += w[j] & 0x04040404u;
+        if (j < 8) s4a += w[j] & 0x10101010u; else s4b += w[j] & 0x10101010u;
+      }
+      if (bad == 0) {
+        const uint32_t n1 = hsum4(s1 >> 1), n2 = hsum4(s2 >> 2), nt = hsum4((s4a >> 4) + (s4b >> 4));   // byte sums <= 64: no carry out of hsum4
+        cT += nt; cG += n2 - nt; cC += n1 - (n2 - nt); cA += NT_CHUNK - n1 - nt;
+      } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          uint32_t t = w[j] & 0x07070707u;
-          t |= t >> 4;
-          const uint32_t sel = __byte_perm(t, 0u, 0x4420);       // the four 3-bit indices as selector nibbles
-          const uint32_t expect = __byte_perm(0x43FF41FFu, 0x47FFFF54u, sel);
-          bad |= w[j] ^ expect;
-          const uint32_t b1 = w[j] >> 1, b2 = w[j] >> 2;
-          s1 += b1 & 0x01010101u; s2 += b2 & 0x01010101u; sg += b1 & b2 & 0x01010101u;
-        }
-        if (bad == 0) {
-          const uint32_t n1 = hsum4(s1), n2 = hsum4(s2), ng = hsum4(sg);
-          cG += ng; cC += n1 - ng; cT += n2 - ng; cA += NT_CHUNK - n1 - n2 + ng;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int first = j * 4;
-            uint32_t x = w[j];
-            if (left < first + 4) {               // last chunk of the scaffold: whatever the padding holds is not sequence
-              const int keep = (int)(left - first);
-              x = keep <= 0 ? 0u : (x & ((1u << (8 * keep)) - 1u));
-            }
-            const uint32_t up = x & 0xDFDFDFDFu;             // 'a' -> 'A'; no other byte maps onto a letter tested below
-            cA += __popc(eq4(up, 0x41414141u));
-            cC += __popc(eq4(up, 0x43434343u));
-            cG += __popc(eq4(up, 0x47474747u));
-            cT += __popc(eq4(up, 0x54545454u)) + __popc(eq4(up, 0x55555555u));
-            const uint32_t fN = eq4(x, 0x4E4E4E4Eu);
-            cN += __popc(fN);
-            cn += __popc(eq4(x, 0x6E6E6E6Eu));
-            m |= (unsigned long long)nibble(fN) << first;
+          const int first = (((j >> 2) + rot) & 3) * 16 + (j & 3) * 4;      // where the word sits in the chunk
+          uint32_t x = w[j];
+          if (left < first + 4) {               // last chunk of the scaffold: whatever the padding holds is not sequence
+            const int keep = left - first;
+            x = keep <= 0 ? 0u : (x & ((1u << (8 * keep)) - 1u));
           }
+          const uint32_t up = x & 0xDFDFDFDFu;             // 'a' -> 'A'; no other byte maps onto a letter tested below
+          cA += __popc(eq4(up, 0x41414141u));
+          cC += __popc(eq4(up, 0x43434343u));
+          cG += __popc(eq4(up, 0x47474747u));
+          cT += __popc(eq4(up, 0x54545454u)) + __popc(eq4(up, 0x55555555u));
+          const uint32_t fN = eq4(x, 0x4E4E4E4Eu);
+          cN += __popc(fN);
+          cn += __popc(eq4(x, 0x6E6E6E6Eu));
+          m |= (unsigned long long)nibble(fN) << first;
         }
       }
-      s_m[tid] = m;
-      __syncthreads();
-      // halo: is-N of the 9 bytes before this chunk and of the byte after it
-      unsigned long long prev9 = 0, nextbit = 0;
-      if (tid > 0) prev9 = s_m[tid - 1] >> 55;
-      else if (pos > 0 && pos < L) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(base + pos - 16));
-        const uint32_t bits = nibble(eq4(v.y, 0x4E4E4E4Eu)) | (nibble(eq4(v.z, 0x4E4E4E4Eu)) << 4) | (nibble(eq4(v.w, 0x4E4E4E4Eu)) << 8);
-        prev9 = bits >> 3;                                   // bytes pos-12..pos-1 -> the last nine
-      }
-      if (tid < NT_THREADS - 1) nextbit = s_m[tid + 1] & 1ull;
-      else if (pos + NT_CHUNK < L) nextbit = base[pos + NT_CHUNK] == 'N';
+    }
+    // halo: is-N of the 9 bytes before this chunk and of the byte after it
+    const uint32_t up9 = __shfl_up_sync(0xffffffffu, (uint32_t)(m >> 55), 1);
+    const uint32_t dn1 = __shfl_down_sync(0xffffffffu, (uint32_t)(m & 1ull), 1);
+    const unsigned long long prev9 = lane > 0 ? up9 : (halo_bits >> 3);       // lane 0: bytes -12..-1 -> the last nine
+    const unsigned long long nextbit = lane < 31 ? dn1 : halo_bits;
+    if (!__any_sync(0xffffffffu, (m | prev9) != 0ull)) {
+      carry += (uint32_t)nbytes;                                 // not an N in sight: the whole row belongs to the open contig
+    } else {
       unsigned long long ends = 0;
       if (m | prev9) {
         const unsigned __int128 X = ((unsigned __int128)m << 9) | (unsigned __int128)prev9;
         const unsigned __int128 A = X & (X >> 1), B = A & (A >> 2), C8 = B & (B >> 4);
-        const unsigned long long run10 = (unsigned long long)(C8 & (A >> 8));   // bit k: bytes pos+k-9 .. pos+k are all N
+        const unsigned long long run10 = (unsigned long long)(C8 & (A >> 8));   // bit i: bytes i-9 .. i of the chunk are all N
         ends = run10 & ~((m >> 1) | (nextbit << 63)) & valid;
       }
       const unsigned long long bases = valid & ~m;
-      // contig index of the chunk's first byte, relative to the tile: exclusive scan of the run ends
-      const uint32_t nb = __popcll(ends);
-      uint32_t incl = nb;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
-      if (lane == 31) s_wsum[warp] = incl;
-      __syncthreads();
-      uint32_t before = 0, total = 0;
-#pragma unroll
-      for (int w8 = 0; w8 < NT_WARPS; ++w8) { const uint32_t v = s_wsum[w8]; if (w8 < warp) before += v; total += v; }
-      uint32_t id = before + incl - nb;
-      if (__all_sync(0xffffffffu, nb == 0)) {                // the whole warp lies inside one contig
-        uint32_t c = __popcll(bases);
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-        if (lane == 0 && c) atomicAdd(&s_acc[id], c);
-      } else {
+      // per lane: bases up to its first run end (all of them if it has none), bases after its last; contigs between two run
+      // ends of the same lane are complete and reported here
+      const bool has = ends != 0ull;
+      uint32_t pre = __popcll(bases), post = 0;
+      if (has) {
         unsigned long long rest = bases, e = ends;
+        int b = __ffsll((long long)e) - 1;
+        unsigned long long upto = b == 63 ? ~0ull : ((2ull << b) - 1ull);
+        pre = __popcll(rest & upto); rest &= ~upto; e &= e - 1;
         while (e) {
-          const int b = __ffsll((long long)e) - 1;
-          const unsigned long long upto = b == 63 ? ~0ull : ((2ull << b) - 1ull);
-          const uint32_t c = __popcll(rest & upto);
-          if (c) atomicAdd(&s_acc[id], c);
-          rest &= ~upto; e &= e - 1; ++id;
+          b = __ffsll((long long)e) - 1;
+          upto = b == 63 ? ~0ull : ((2ull << b) - 1ull);
+          nt_emit(p, s, __popcll(rest & upto));
+          rest &= ~upto; e &= e - 1;
         }
-        const uint32_t c = __popcll(rest);
-        if (c) atomicAdd(&s_acc[id], c);
+        post = __popcll(rest);
       }
-      __syncthreads();
-      // contigs 0 .. total-1 of this tile are closed; the last index stays open into the next tile.  The first contig the
-      // segment closes may have begun in the segment before: it is the segment's head, joined on the host.
-      if (total > 0 && !closed) head = s_acc[0] + carry;
-      for (uint32_t j = tid; j < total; j += NT_THREADS) {
-        if (j == 0 && !closed) continue;
-        const uint32_t len = s_acc[j] + (j == 0 ? carry : 0u);
-        if (len) {
-          const unsigned long long at = atomicAdd(p.ncontigs, 1ull);
-          if ((long long)at < p.cap) { p.contig_scaf[at] = (uint32_t)s; p.contig_len[at] = len; }
-          ++my_ctg; my_ctg_bases += len;
-        }
+      // open bases arriving at each lane: scan of (has, value) with  (h1,v1) then (h2,v2) = (h1|h2, h2 ? v2 : v1+v2)
+      uint32_t sh = has ? 1u : 0u, sv = has ? post : pre;
+#pragma unroll
+      for (int dd = 1; dd < 32; dd <<= 1) {
+        const uint32_t oh = __shfl_up_sync(0xffffffffu, sh, dd), ov = __shfl_up_sync(0xffffffffu, sv, dd);
+        if (lane >= dd) { sv = sh ? sv : ov + sv; sh |= oh; }
       }
-      carry = s_acc[total] + (total == 0 ? carry : 0u);
-      closed = closed || total > 0;
-      __syncthreads();
-      for (uint32_t j = tid; j <= total; j += NT_THREADS) s_acc[j] = 0;
-      // the next tile's first barrier orders these stores before its atomics
+      uint32_t eh = __shfl_up_sync(0xffffffffu, sh, 1), ev = __shfl_up_sync(0xffffffffu, sv, 1);   // exclusive
+      if (lane == 0) { eh = 0; ev = 0; }
+      const uint32_t open_in = eh ? ev : carry + ev;
+      const bool is_head = has && !closed && !eh;               // the first run end of the piece: at most one lane
+      if (has && !is_head) nt_emit(p, s, open_in + pre);
+      const uint32_t head_src = __ballot_sync(0xffffffffu, is_head);
+      if (head_src) head = __shfl_sync(0xffffffffu, open_in + pre, __ffs(head_src) - 1);
+      const uint32_t th = __shfl_sync(0xffffffffu, sh, 31), tv = __shfl_sync(0xffffffffu, sv, 31);
+      carry = th ? tv : carry + tv;
+      closed = closed || th;
     }
-    if (tid == 0) { NtSegment r; r.head = head; r.tail = carry; r.closed = closed ? 1u : 0u; p.seg[item] = r; }
-    unsigned long long v[8] = {cA, cC, cG, cT, cN, cn, my_ctg, my_ctg_bases};
+    if (last_row || k + 1 == hi) {
+      const uint32_t v[6] = {cA, cC, cG, cT, cN, cn};
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      unsigned long long x = v[k];
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-      if (lane == 0 && x) atomicAdd(&s_tot[k], x);
+      for (int i = 0; i < 6; ++i) { const uint32_t x = __reduce_add_sync(0xffffffffu, v[i]); if (lane == i && x) atomicAdd(&p.stats[(size_t)s * 8 + i], (unsigned long long)x); }
+      if (lane == 0) { NtPiece r; r.head = head; r.tail = carry; r.closed = closed ? 1u : 0u; r.pad = 0; p.piece[(size_t)s + gw] = r; }
+      cA = cC = cG = cT = cN = cn = 0; carry = 0; head = 0; closed = false;
     }
-    __syncthreads();
-    if (tid < 8) { if (s_tot[tid]) atomicAdd(&p.stats[(size_t)s * 8 + tid], s_tot[tid]); s_tot[tid] = 0; }
-    // s_next is rewritten by thread 0 only after the barrier at the top of the loop, which also orders the s_tot reset
-    __syncthreads();
   }
 }
 
@@ -289,57 +309,68 @@ int ckm_scaffold_stats(ckm_engine *e, const uint8_t *bytes, int64_t nbytes, cons
   cudaSetDevice(e->device);
   PoolScope pool_scope(e);
   cudaStream_t st = e->stream;
-  std::vector<int32_t> seg_scaf; std::vector<int64_t> seg_off;
+  std::vector<NtRow> rows;
+  rows.reserve((size_t)(nbytes / NT_ROW) + nscaf);
   for (int32_t s = 0; s < nscaf; ++s)
-    for (int64_t off = 0; off < lens[s]; off += NT_SEG) { seg_scaf.push_back(s); seg_off.push_back(off); }
-  const int64_t nseg = (int64_t)seg_scaf.size();
+    for (int64_t off = 0; off < lens[s]; off += NT_ROW) {
+      const int64_t n = std::min<int64_t>(NT_ROW, lens[s] - off);
+      NtRow r; r.src = starts[s] + off; r.scaf = (uint32_t)s;
+      r.info = (uint32_t)n | (off == 0 ? 1u << 30 : 0u) | (off + NT_ROW >= lens[s] ? 1u << 31 : 0u);
+      rows.push_back(r);
+    }
+  const int64_t nrows = (int64_t)rows.size();
   std::memset(stats_out, 0, sizeof(int64_t) * 8 * nscaf);
-  if (nseg == 0) return CKM_OK;
-  if (nseg > 0x7FFFFFFFll) { set_error("ckm_scaffold_stats: too many bytes for one call"); return CKM_EINVAL; }
-  DevBuf dbytes, dstarts, dlens, dsegs, dsego, dseg, dstats, dcs, dcl, dctr;
+  if (nrows == 0) return CKM_OK;
+  const int grid = (int)std::min<int64_t>((int64_t)e->prop.multiProcessorCount * NT_CTAS_PER_SM, (nrows + NT_WARPS - 1) / NT_WARPS);
+  const int64_t nwarps = (int64_t)grid * NT_WARPS;
+  const size_t npiece = (size_t)nscaf + nwarps;
+  DevBuf dbytes, drows, dpiece, dstats, dcs, dcl, dctr;
   int rc;
-  if ((rc = dbytes.alloc((size_t)nbytes + 64)) || (rc = dstarts.alloc(sizeof(int64_t) * nscaf)) || (rc = dlens.alloc(sizeof(int64_t) * nscaf)) ||
-      (rc = dsegs.alloc(sizeof(int32_t) * nseg)) || (rc = dsego.alloc(sizeof(int64_t) * nseg)) || (rc = dseg.alloc(sizeof(NtSegment) * nseg)) ||
+  if ((rc = dbytes.alloc((size_t)nbytes + 64)) || (rc = drows.alloc(sizeof(NtRow) * nrows)) || (rc = dpiece.alloc(sizeof(NtPiece) * npiece)) ||
       (rc = dstats.alloc(sizeof(int64_t) * 8 * nscaf)) ||
       (rc = dcs.alloc(sizeof(uint32_t) * (size_t)contig_cap)) || (rc = dcl.alloc(sizeof(uint32_t) * (size_t)contig_cap)) || (rc = dctr.alloc(64)))
     return rc;
   CKM_CUDA(cudaMemcpyAsync(dbytes.p, bytes, (size_t)nbytes, cudaMemcpyHostToDevice, st));
-  CKM_CUDA(cudaMemcpyAsync(dstarts.p, starts, sizeof(int64_t) * nscaf, cudaMemcpyHostToDevice, st));
-  CKM_CUDA(cudaMemcpyAsync(dlens.p, lens, sizeof(int64_t) * nscaf, cudaMemcpyHostToDevice, st));
-  CKM_CUDA(cudaMemcpyAsync(dsegs.p, seg_scaf.data(), sizeof(int32_t) * nseg, cudaMemcpyHostToDevice, st));
-  CKM_CUDA(cudaMemcpyAsync(dsego.p, seg_off.data(), sizeof(int64_t) * nseg, cudaMemcpyHostToDevice, st));
+  CKM_CUDA(cudaMemcpyAsync(drows.p, rows.data(), sizeof(NtRow) * nrows, cudaMemcpyHostToDevice, st));
+  CKM_CUDA(cudaMemsetAsync(dpiece.p, 0, sizeof(NtPiece) * npiece, st));
   CKM_CUDA(cudaMemsetAsync(dctr.p, 0, 64, st));
   CKM_CUDA(cudaMemsetAsync(dstats.p, 0, sizeof(int64_t) * 8 * nscaf, st));
   NtParams p;
-  p.bytes = dbytes.as<uint8_t>(); p.starts = dstarts.as<int64_t>(); p.lens = dlens.as<int64_t>();
-  p.seg_scaf = dsegs.as<int32_t>(); p.seg_off = dsego.as<int64_t>(); p.nseg = (int32_t)nseg; p.seg = dseg.as<NtSegment>();
-  p.work = dctr.as<int32_t>(); p.stats = dstats.as<unsigned long long>();
+  p.bytes = dbytes.as<uint8_t>(); p.rows = drows.as<NtRow>(); p.nrows = nrows; p.piece = dpiece.as<NtPiece>();
+  p.stats = dstats.as<unsigned long long>();
   p.contig_scaf = dcs.as<uint32_t>(); p.contig_len = dcl.as<uint32_t>();
   p.ncontigs = reinterpret_cast<unsigned long long *>(dctr.as<uint8_t>() + 8); p.cap = contig_cap;
-  const int per_sm = 4;                                        // 4 x 256 threads at <= 64 registers
-  const int grid = (int)std::min<int64_t>((int64_t)e->prop.multiProcessorCount * per_sm, nseg);
+  const int dyn_smem = NT_WARPS * NT_STAGES * NT_STAGE;
+  static bool attr_set = false;
+  if (!attr_set) { CKM_CUDA(cudaFuncSetAttribute(ntstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem)); attr_set = true; }
   CKM_CUDA(cudaEventRecord(e->ev[0], st));
-  ntstats_kernel<<<grid, NT_THREADS, 0, st>>>(p);
+  ntstats_kernel<<<grid, NT_THREADS, dyn_smem, st>>>(p);
   CKM_CUDA(cudaGetLastError());
   CKM_CUDA(cudaEventRecord(e->ev[1], st));
   unsigned long long n_dev = 0;
-  std::vector<NtSegment> seg((size_t)nseg);
+  std::vector<NtPiece> piece(npiece);
   CKM_CUDA(cudaMemcpyAsync(&n_dev, p.ncontigs, sizeof(n_dev), cudaMemcpyDeviceToHost, st));
   CKM_CUDA(cudaMemcpyAsync(stats_out, dstats.p, sizeof(int64_t) * 8 * nscaf, cudaMemcpyDeviceToHost, st));
-  CKM_CUDA(cudaMemcpyAsync(seg.data(), dseg.p, sizeof(NtSegment) * nseg, cudaMemcpyDeviceToHost, st));
+  CKM_CUDA(cudaMemcpyAsync(piece.data(), dpiece.p, sizeof(NtPiece) * npiece, cudaMemcpyDeviceToHost, st));
   CKM_CUDA(cudaStreamSynchronize(st));
   if (kernel_ms_out) CKM_CUDA(cudaEventElapsedTime(kernel_ms_out, e->ev[0], e->ev[1]));
-  // join the open ends of the segments: a contig runs from the tail of one segment through every segment without a run
-  // end into the head of the next one that has one
+  // join the open ends of the pieces, in list order: a contig runs from the tail of one piece through every piece without a
+  // run end into the head of the next one of the same scaffold that has one
   std::vector<std::pair<uint32_t, uint32_t>> joined;
-  for (int64_t i = 0; i < nseg;) {
-    const int32_t s = seg_scaf[i];
-    uint64_t open = 0;
-    for (; i < nseg && seg_scaf[i] == s; ++i) {
-      if (seg[i].closed) { if (open + seg[i].head) joined.emplace_back((uint32_t)s, (uint32_t)(open + seg[i].head)); open = seg[i].tail; }
-      else open += seg[i].tail;
+  {
+    int64_t cur = -1; uint64_t open = 0;
+    for (int64_t c = 0; c < nwarps; ++c) {
+      const int64_t lo = nrows * c / nwarps, hi = nrows * (c + 1) / nwarps;
+      if (lo >= hi) continue;
+      for (int64_t s = rows[lo].scaf; s <= (int64_t)rows[hi - 1].scaf; ++s) {
+        if (lens[s] == 0) continue;
+        if (s != cur) { if (open) joined.emplace_back((uint32_t)cur, (uint32_t)open); cur = s; open = 0; }
+        const NtPiece &r = piece[(size_t)s + c];
+        if (r.closed) { if (open + r.head) joined.emplace_back((uint32_t)s, (uint32_t)(open + r.head)); open = r.tail; }
+        else open += r.tail;
+      }
     }
-    if (open) joined.emplace_back((uint32_t)s, (uint32_t)open);
+    if (open) joined.emplace_back((uint32_t)cur, (uint32_t)open);
   }
   const int64_t n_found = (int64_t)n_dev + (int64_t)joined.size();
   *ncontigs_out = n_found;

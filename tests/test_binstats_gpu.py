@@ -84,6 +84,9 @@ def test_scan_on_boundaries(engine):
     for n in (0, 1, 9, 10, 11, 63, 64, 65, 16383, 16384, 16385, 131071, 131072, 131073, 400000):
         seqs.append(b'N' * n)
         seqs.append(b'A' * n)
+        seqs.append(b'G' * n)
+        seqs.append(b'TG' * (n // 2))
+        seqs.append(b'C' * n)
         seqs.append((b'N' * 10 + b'C') * (n // 11) + b'N' * (n % 11))
     _check_against_oracle(engine, seqs)
     _check_against_oracle(engine, seqs[::7], pad_byte=ord('N'))         # whatever lies in the padding is not sequence
