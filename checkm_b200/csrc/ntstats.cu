@@ -30,7 +30,13 @@ constexpr int NT_ROW = 32 * NT_CHUNK;                // 2 KB: what a warp takes 
 constexpr int NT_HALO = 16;                          // bytes staged either side of a row (9 before and 1 after are looked at)
 constexpr int NT_STAGE = NT_HALO + NT_ROW + NT_HALO;
 constexpr int NT_STAGES = 3;                         // rows in flight per warp
-constexpr int NT_CTAS_PER_SM = 4;                    // 32 warps x 3 x 2 KB of stages = 195 KB of shared memory, <= 64 registers
+constexpr int NT_DESC_OFF = NT_STAGES * NT_STAGE;    // per-warp shared memory: the stages, their row descriptors, their mbarriers
+constexpr int NT_BAR_OFF = NT_DESC_OFF + NT_STAGES * 16;
+constexpr int NT_WARP_SMEM = (NT_BAR_OFF + NT_STAGES * 8 + 127) / 128 * 128;
+#ifndef CKM_NT_CTAS
+#define CKM_NT_CTAS 4
+#endif
+constexpr int NT_CTAS_PER_SM = CKM_NT_CTAS;          // 4: 32 warps x 3 x 2 KB of stages = 200 KB of shared memory, <= 64 registers
 
 // The scaffolds of a call, cut into 2 KB rows, form one list; every warp of the grid takes a contiguous range of it and
 // streams its rows through its own ring of shared-memory stages, filled by TMA bulk copies that lane 0 issues NT_STAGES
@@ -38,7 +44,9 @@ constexpr int NT_CTAS_PER_SM = 4;                    // 32 warps x 3 x 2 KB of s
 // inside a piece are reported by the kernel; the bases before the first run end of a piece (head) and after its last (tail)
 // come back separately and the host joins tail + head across the cuts (ckm_scaffold_stats below).
 // Piece index = scaffold + warp: along the list one of the two grows at every cut.
-struct NtRow { int64_t src; uint32_t scaf; uint32_t info; };       // info: valid bytes (1..2048) | first row << 30 | last row << 31
+// src: device address the row's copy starts at (16 bytes before the row unless it is the first of its scaffold);
+// info: valid bytes (1..2048) | 16-byte units of the copy << 12 | first row << 30 | last row << 31
+struct NtRow { uint64_t src; uint32_t scaf; uint32_t info; };
 struct NtPiece { uint32_t head, tail, closed, pad; };              // closed: the piece holds at least one run end
 
 struct NtParams {
@@ -63,14 +71,25 @@ __device__ __forceinline__ uint32_t nibble(uint32_t flags) { return (((flags >> 
 // sum of the four bytes of x (the sum must stay below 256)
 __device__ __forceinline__ uint32_t hsum4(uint32_t x) { return (x * 0x01010101u) >> 24; }
 
-__device__ __forceinline__ void nt_issue(const NtParams &p, const NtRow d, uint32_t stage, NtRow *desc, uint64_t *bar) {
-  *desc = d;
-  const uint32_t nbytes = d.info & 0xFFFFu;
-  const uint32_t left = (d.info >> 30) & 1u ? 0u : (uint32_t)NT_HALO, right = (d.info >> 31) ? 0u : (uint32_t)NT_HALO;
-  const uint32_t bytes = left + (nbytes + 63u) / 64u * 64u + right;
-  fence_proxy_async();                                    // the stage was read through the generic proxy a moment ago
-  mbar_expect_tx(bar, bytes);
-  bulk_g2s(stage + NT_HALO - left, p.bytes + d.src - left, bytes, bar);
+// lane 0: hand a stage to the copy engine.  Every value loaded from the stage has been used by now, so the loads are done.
+__device__ __forceinline__ void nt_issue(const NtRow d, uint32_t stage, uint32_t desc, uint32_t bar) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(desc), "r"((uint32_t)d.src), "r"((uint32_t)(d.src >> 32)), "r"(d.scaf), "r"(d.info) : "memory");
+  const uint32_t bytes = ((d.info >> 12) & 0xFFu) * 16u;
+  fence_proxy_async();
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(stage + (((d.info >> 30) & 1u) ? (uint32_t)NT_HALO : 0u)),
+               "l"(d.src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void nt_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "NT_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra NT_DONE;\n"
+      "bra NT_WAIT;\n"
+      "NT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
 __device__ __forceinline__ void nt_emit(const NtParams &p, uint32_t scaf, uint32_t len) {
@@ -82,20 +101,20 @@ __device__ __forceinline__ void nt_emit(const NtParams &p, uint32_t scaf, uint32
 }
 
 __global__ void __launch_bounds__(NT_THREADS, NT_CTAS_PER_SM) ntstats_kernel(NtParams p) {
-  extern __shared__ __align__(128) uint8_t s_stage[];           // NT_WARPS x NT_STAGES x NT_STAGE
-  __shared__ __align__(16) NtRow s_desc[NT_WARPS][NT_STAGES];
-  __shared__ __align__(8) uint64_t s_bar[NT_WARPS][NT_STAGES];
+  extern __shared__ __align__(128) uint8_t s_dyn[];             // NT_WARPS x NT_WARP_SMEM
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long gw = (long long)blockIdx.x * NT_WARPS + warp, nw = (long long)gridDim.x * NT_WARPS;
   const long long lo = p.nrows * gw / nw, hi = p.nrows * (gw + 1) / nw;
   if (lo >= hi) return;
-  const uint32_t ring = smem_u32(s_stage) + warp * (NT_STAGES * NT_STAGE);
+  const int n = (int)(hi - lo);                                  // rows of this warp (the host keeps a call below 2^31 rows)
+  const NtRow *mine = p.rows + lo;
+  const uint32_t ring = smem_u32(s_dyn) + warp * NT_WARP_SMEM;     // stage i at ring + i * NT_STAGE
   NtRow upcoming = {0, 0u, 0u};                                  // lane 0: the row to issue next, fetched one row early
   if (lane == 0) {
-    for (int i = 0; i < NT_STAGES; ++i) mbar_init(&s_bar[warp][i], 1);
+    for (int i = 0; i < NT_STAGES; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ring + NT_BAR_OFF + i * 8) : "memory");
     fence_mbar_init();
-    for (int i = 0; i < NT_STAGES && lo + i < hi; ++i) nt_issue(p, p.rows[lo + i], ring + i * NT_STAGE, &s_desc[warp][i], &s_bar[warp][i]);
-    if (lo + NT_STAGES < hi) upcoming = p.rows[lo + NT_STAGES];
+    for (int i = 0; i < NT_STAGES && i < n; ++i) nt_issue(mine[i], ring + i * NT_STAGE, ring + NT_DESC_OFF + i * 16, ring + NT_BAR_OFF + i * 8);
+    if (NT_STAGES < n) upcoming = mine[NT_STAGES];
   }
   __syncwarp();
   const int rot = (lane >> 1) & 3;                               // the lane reads its four 16-byte vectors starting at this one:
@@ -104,12 +123,13 @@ __global__ void __launch_bounds__(NT_THREADS, NT_CTAS_PER_SM) ntstats_kernel(NtP
   uint32_t carry = 0;                                            // bases of the contig still open (same in every lane)
   uint32_t head = 0; bool closed = false;                        // same in every lane
   int st = 0; uint32_t phase = 0;
-  for (long long k = lo; k < hi; ++k) {
-    mbar_wait(&s_bar[warp][st], phase);
-    const NtRow d = s_desc[warp][st];
-    const uint32_t s = d.scaf;
-    const int nbytes = (int)(d.info & 0xFFFFu);
-    const bool first_row = (d.info >> 30) & 1u, last_row = (d.info >> 31) != 0;
+  uint32_t tail9 = 0;                                            // lane 0: is-N of the nine bytes before the row
+  for (int k = 0; k < n; ++k) {
+    nt_wait(ring + NT_BAR_OFF + st * 8, phase);
+    const uint4 d = lds128(ring + NT_DESC_OFF + st * 16);
+    const uint32_t s = d.z;
+    const int nbytes = (int)(d.w & 0xFFFu);
+    const bool first_row = (d.w >> 30) & 1u, last_row = (d.w >> 31) != 0;
     const uint32_t body = ring + st * NT_STAGE + NT_HALO;
     const int left = nbytes - lane * NT_CHUNK;                   // bytes of the scaffold in and after this lane's chunk
     uint32_t w[16];
@@ -118,48 +138,51 @@ __global__ void __launch_bounds__(NT_THREADS, NT_CTAS_PER_SM) ntstats_kernel(NtP
       const uint4 v = lds128(body + lane * NT_CHUNK + ((q + rot) & 3) * 16);
       w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
     }
-    // the two halo bytes groups, read before the stage is handed back: is-N of the 12 bytes before the row, of the byte after
+    // halo, read before the stage is handed back: is-N of the byte after the row, and -- only at the first row of this warp's
+    // range, afterwards the previous row's mask is at hand -- of the 12 bytes before it
     uint32_t halo_bits = 0;
-    if (lane == 0 && !first_row) {
+    if (k == 0 && lane == 0 && !first_row) {
       const uint4 v = lds128(body - NT_HALO);
       halo_bits = nibble(eq4(v.y, 0x4E4E4E4Eu)) | (nibble(eq4(v.z, 0x4E4E4E4Eu)) << 4) | (nibble(eq4(v.w, 0x4E4E4E4Eu)) << 8);
+      tail9 = halo_bits >> 3;                                    // bytes -12..-1 -> the last nine
     }
-    if (lane == 31 && !last_row) halo_bits = s_stage[warp * (NT_STAGES * NT_STAGE) + st * NT_STAGE + NT_HALO + NT_ROW] == 'N';
-    __syncwarp();
-    // every lane holds its bytes in registers: the stage can take the row NT_STAGES further on
-    if (lane == 0 && k + NT_STAGES < hi) {
-      nt_issue(p, upcoming, ring + st * NT_STAGE, &s_desc[warp][st], &s_bar[warp][st]);
-      if (k + NT_STAGES + 1 < hi) upcoming = p.rows[k + NT_STAGES + 1];
-    }
-    if (++st == NT_STAGES) { st = 0; phase ^= 1u; }
+    if (lane == 31 && !last_row) halo_bits = s_dyn[warp * NT_WARP_SMEM + st * NT_STAGE + NT_HALO + NT_ROW] == 'N';
 
     unsigned long long m = 0, valid = 0;
     if (left > 0) {
       valid = left >= NT_CHUNK ? ~0ull : ((1ull << left) - 1ull);
+      if (left < NT_CHUNK) {                    // last chunk of the scaffold: whatever the padding holds is not sequence;
+#pragma unroll                                  // count it as 'A' here and take it off again below
+        for (int j = 0; j < 16; ++j) {
+          const int keep = left - ((((j >> 2) + rot) & 3) * 16 + (j & 3) * 4);   // bytes of this word inside the scaffold
+          if (keep < 4) { const uint32_t in = keep <= 0 ? 0u : ((1u << (8 * keep)) - 1u); w[j] = (w[j] & in) | (0x41414141u & ~in); }
+        }
+      }
       // Fast path, a chunk of nothing but upper-case A C G T (what assemblies mostly are): the low three bits of the
       // four letters differ (A 1, C 3, T 4, G 7), so one byte permute looks up the letter each byte would have to be and
-      // one xor tells whether it is.  Then bit 1 is set in C and G, bit 2 in G and T, bit 4 in T only.
-      uint32_t bad = left >= NT_CHUNK ? 0u : 1u;
-      uint32_t s1 = 0, s2 = 0, s4a = 0, s4b = 0;               // per-byte sums over the words of 2 x bit1, 4 x bit2, 16 x bit4 (two halves)
+      // one xor tells whether it is.  Two more permutes by the same index look up what the byte adds to the counts:
+      // 0x01 for C, 0x10 for G in one table (two 4-bit counters per byte lane, 8 words each), 0x01 for T in the other.
+      uint32_t bad = 0, cg0 = 0, cg1 = 0, tt = 0;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         uint32_t t = w[j] & 0x07070707u;
         t |= t >> 4;
-        const uint32_t sel = __byte_perm(t, 0u, 0x4420);       // the four 3-bit indices as selector nibbles
-        const uint32_t expect = __byte_perm(0x43FF41FFu, 0x47FFFF54u, sel);
-        bad |= w[j] ^ expect;
-        s1 += w[j] & 0x02020202u; s2 += w[j] & 0x04040404u;
-        if (j < 8) s4a += w[j] & 0x10101010u; else s4b += w[j] & 0x10101010u;
+        const uint32_t sel = prmt_b32(t, 0u, 0x4420);           // the four 3-bit indices as selector nibbles (all below 8)
+        bad |= w[j] ^ prmt_b32(0x43FF41FFu, 0x47FFFF54u, sel);
+        const uint32_t cg = prmt_b32(0x01000000u, 0x10000000u, sel);
+        if (j < 8) cg0 += cg; else cg1 += cg;
+        tt += prmt_b32(0u, 0x00000001u, sel);
       }
       if (bad == 0) {
-        const uint32_t n1 = hsum4(s1 >> 1), n2 = hsum4(s2 >> 2), nt = hsum4((s4a >> 4) + (s4b >> 4));   // byte sums <= 64: no carry out of hsum4
-        cT += nt; cG += n2 - nt; cC += n1 - (n2 - nt); cA += NT_CHUNK - n1 - nt;
+        const uint32_t nc = hsum4((cg0 & 0x0F0F0F0Fu) + (cg1 & 0x0F0F0F0Fu)), ng = hsum4(((cg0 >> 4) & 0x0F0F0F0Fu) + ((cg1 >> 4) & 0x0F0F0F0Fu));
+        const uint32_t nt = hsum4(tt);
+        cC += nc; cG += ng; cT += nt; cA += (uint32_t)min(left, NT_CHUNK) - nc - ng - nt;
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int first = (((j >> 2) + rot) & 3) * 16 + (j & 3) * 4;      // where the word sits in the chunk
           uint32_t x = w[j];
-          if (left < first + 4) {               // last chunk of the scaffold: whatever the padding holds is not sequence
+          if (left < first + 4) {               // the padding stand-ins again
             const int keep = left - first;
             x = keep <= 0 ? 0u : (x & ((1u << (8 * keep)) - 1u));
           }
@@ -178,8 +201,9 @@ __global__ void __launch_bounds__(NT_THREADS, NT_CTAS_PER_SM) ntstats_kernel(NtP
     // halo: is-N of the 9 bytes before this chunk and of the byte after it
     const uint32_t up9 = __shfl_up_sync(0xffffffffu, (uint32_t)(m >> 55), 1);
     const uint32_t dn1 = __shfl_down_sync(0xffffffffu, (uint32_t)(m & 1ull), 1);
-    const unsigned long long prev9 = lane > 0 ? up9 : (halo_bits >> 3);       // lane 0: bytes -12..-1 -> the last nine
-    const unsigned long long nextbit = lane < 31 ? dn1 : halo_bits;
+    const uint32_t after = __shfl_sync(0xffffffffu, halo_bits, 31);           // (also: the halo byte has been loaded and used)
+    const unsigned long long prev9 = lane > 0 ? up9 : (first_row ? 0u : tail9);
+    const unsigned long long nextbit = lane < 31 ? dn1 : after;
     if (!__any_sync(0xffffffffu, (m | prev9) != 0ull)) {
       carry += (uint32_t)nbytes;                                 // not an N in sight: the whole row belongs to the open contig
     } else {
@@ -226,7 +250,14 @@ __global__ void __launch_bounds__(NT_THREADS, NT_CTAS_PER_SM) ntstats_kernel(NtP
       carry = th ? tv : carry + tv;
       closed = closed || th;
     }
-    if (last_row || k + 1 == hi) {
+    tail9 = __shfl_sync(0xffffffffu, (uint32_t)(m >> 55), 31);
+    // every value read from the stage has been used: it can take the row NT_STAGES further on
+    if (lane == 0 && k + NT_STAGES < n) {
+      nt_issue(upcoming, ring + st * NT_STAGE, ring + NT_DESC_OFF + st * 16, ring + NT_BAR_OFF + st * 8);
+      if (k + NT_STAGES + 1 < n) upcoming = mine[k + NT_STAGES + 1];
+    }
+    if (++st == NT_STAGES) { st = 0; phase ^= 1u; }
+    if (last_row || k + 1 == n) {
       const uint32_t v[6] = {cA, cC, cG, cT, cN, cn};
 #pragma unroll
       for (int i = 0; i < 6; ++i) { const uint32_t x = __reduce_add_sync(0xffffffffu, v[i]); if (lane == i && x) atomicAdd(&p.stats[(size_t)s * 8 + i], (unsigned long long)x); }
@@ -309,24 +340,29 @@ int ckm_scaffold_stats(ckm_engine *e, const uint8_t *bytes, int64_t nbytes, cons
   cudaSetDevice(e->device);
   PoolScope pool_scope(e);
   cudaStream_t st = e->stream;
+  DevBuf dbytes;
+  { int rc0 = dbytes.alloc((size_t)nbytes + 64); if (rc0) return rc0; }
   std::vector<NtRow> rows;
   rows.reserve((size_t)(nbytes / NT_ROW) + nscaf);
   for (int32_t s = 0; s < nscaf; ++s)
     for (int64_t off = 0; off < lens[s]; off += NT_ROW) {
       const int64_t n = std::min<int64_t>(NT_ROW, lens[s] - off);
-      NtRow r; r.src = starts[s] + off; r.scaf = (uint32_t)s;
-      r.info = (uint32_t)n | (off == 0 ? 1u << 30 : 0u) | (off + NT_ROW >= lens[s] ? 1u << 31 : 0u);
+      const bool first = off == 0, last = off + NT_ROW >= lens[s];
+      const int64_t left = first ? 0 : NT_HALO, copy = left + (n + 63) / 64 * 64 + (last ? 0 : NT_HALO);
+      NtRow r; r.src = (uint64_t)(uintptr_t)(dbytes.as<uint8_t>() + starts[s] + off - left); r.scaf = (uint32_t)s;
+      r.info = (uint32_t)n | ((uint32_t)(copy / 16) << 12) | (first ? 1u << 30 : 0u) | (last ? 1u << 31 : 0u);
       rows.push_back(r);
     }
   const int64_t nrows = (int64_t)rows.size();
   std::memset(stats_out, 0, sizeof(int64_t) * 8 * nscaf);
   if (nrows == 0) return CKM_OK;
+  if (nrows > 0x7FFFFFFFll) { set_error("ckm_scaffold_stats: too many bytes for one call"); return CKM_EINVAL; }
   const int grid = (int)std::min<int64_t>((int64_t)e->prop.multiProcessorCount * NT_CTAS_PER_SM, (nrows + NT_WARPS - 1) / NT_WARPS);
   const int64_t nwarps = (int64_t)grid * NT_WARPS;
   const size_t npiece = (size_t)nscaf + nwarps;
-  DevBuf dbytes, drows, dpiece, dstats, dcs, dcl, dctr;
+  DevBuf drows, dpiece, dstats, dcs, dcl, dctr;
   int rc;
-  if ((rc = dbytes.alloc((size_t)nbytes + 64)) || (rc = drows.alloc(sizeof(NtRow) * nrows)) || (rc = dpiece.alloc(sizeof(NtPiece) * npiece)) ||
+  if ((rc = drows.alloc(sizeof(NtRow) * nrows)) || (rc = dpiece.alloc(sizeof(NtPiece) * npiece)) ||
       (rc = dstats.alloc(sizeof(int64_t) * 8 * nscaf)) ||
       (rc = dcs.alloc(sizeof(uint32_t) * (size_t)contig_cap)) || (rc = dcl.alloc(sizeof(uint32_t) * (size_t)contig_cap)) || (rc = dctr.alloc(64)))
     return rc;
@@ -340,7 +376,7 @@ int ckm_scaffold_stats(ckm_engine *e, const uint8_t *bytes, int64_t nbytes, cons
   p.stats = dstats.as<unsigned long long>();
   p.contig_scaf = dcs.as<uint32_t>(); p.contig_len = dcl.as<uint32_t>();
   p.ncontigs = reinterpret_cast<unsigned long long *>(dctr.as<uint8_t>() + 8); p.cap = contig_cap;
-  const int dyn_smem = NT_WARPS * NT_STAGES * NT_STAGE;
+  const int dyn_smem = NT_WARPS * NT_WARP_SMEM;
   static bool attr_set = false;
   if (!attr_set) { CKM_CUDA(cudaFuncSetAttribute(ntstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem)); attr_set = true; }
   CKM_CUDA(cudaEventRecord(e->ev[0], st));
