@@ -159,3 +159,30 @@ def test_search_wide_classes_and_long_models(engine, oracle, tmp_path):
     compare([r for r, _ in blocked], np.array([h for _, h in blocked], dtype=hits.dtype), exact=True)
     compare([r for r, _ in chunked], np.array([h for _, h in chunked], dtype=hits.dtype), exact=False)
     models.close()
+
+
+def test_search_giant_and_tiny_sequences(engine, cpr_models, cpr_oracle, oracle):
+    """One 30,000-residue protein carrying many domains of many families (the worst case of every per-sequence buffer: regions,
+    envelopes, ensemble traces), next to sequences of 1, 2 and 5 residues and ordinary ORFs."""
+    hm = synth.read_hmms(CPR_HMM)
+    b = synth.make_bin('g', hm, seed=41, n_orfs=120, max_len=1500, tandem_prob=0.2)
+    rng = np.random.default_rng(42)
+    parts = []
+    planted = [i for i in range(b.nseq) if b.offsets[i + 1] - b.offsets[i] > 150]
+    while sum(len(p) for p in parts) < 30000:
+        parts.append(b.seq(int(rng.choice(planted))))
+        parts.append(rng.integers(0, 20, size=int(rng.integers(5, 120))).astype(np.uint8))
+    giant = np.concatenate(parts)[:30000]
+    tiny = [np.array([10], dtype=np.uint8), np.array([0, 19], dtype=np.uint8), np.array([3, 3, 3, 3, 3], dtype=np.uint8)]
+    seqs = [b.seq(i) for i in range(40)] + [giant] + tiny + [b.seq(i) for i in range(40, 60)]
+    residues = np.concatenate(seqs)
+    offsets = np.concatenate([[0], np.cumsum([len(s) for s in seqs])]).astype(np.int64)
+    db = engine.seqdb(residues, offsets)
+    hits = engine.search(cpr_models, db)
+    db.close()
+    rp = oracle.search(cpr_oracle, residues, offsets, nthreads=8)
+    rows = oracle.hits_table(rp)
+    oracle.free_results(rp)
+    on_giant = [r for r in rows if r['seqidx'] == 40]
+    assert len(on_giant) >= 20, len(on_giant)
+    print('giant sequence: %d domain rows of %d families; worst score diff %g' % (len(on_giant), len({r['model'] for r in on_giant}), compare(rows, hits)))
