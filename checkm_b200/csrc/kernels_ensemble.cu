@@ -13,15 +13,19 @@
 namespace ckm {
 
 constexpr int NSAMPLES = 200;
-constexpr int SPCAP = 4096;           // sampled segments kept per region
-constexpr int MAXENV = ENS_MAXENV;    // envelopes reported per region
+// Per-region capacities (EnsembleCaps, stages.hpp): sampled segments kept for the clustering, segments of one trace,
+// envelopes reported.  The defaults cover regions of up to ~20 domains; a region that needs more says how much in
+// `need` and the search repeats its domain phase with that region's capacities raised (search.cu).
 
 struct EnsembleParams {
   DomdefParams d;
   const Region *regions; const int32_t *multi_idx; int32_t nmulti;
   const int64_t *scratch_off;         // per multi region, in floats
   float *scratch;
-  Envelope *env_out; int32_t *env_count;      // [nmulti][MAXENV], [nmulti]
+  const EnsembleCaps *caps;           // per multi region
+  const int64_t *env_off;             // per multi region: its first slot in env_out
+  Envelope *env_out; int32_t *env_count;      // env_count: envelopes written, or -1 when a capacity was exceeded
+  int32_t *need;                      // per multi region x 3: sampled segments, most segments in one trace, significant clusters
 };
 
 enum { ST_M = 1, ST_D, ST_I, ST_S, ST_N, ST_B, ST_E, ST_C, ST_T, ST_J };
@@ -88,10 +92,13 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) ensemble_kernel(EnsembleParams
     float *F = ep.scratch + ep.scratch_off[ri];
     float *xf = F + (int64_t)(Lr + 1) * 3 * Mpad;
     float *acc = xf + (int64_t)(Lr + 1) * X_NX, *val = acc + (Lr + 1);
+    const EnsembleCaps cap = ep.caps[ri];
+    const int SPCAP = cap.segments, TRCAP = cap.trace_segments, MAXENV = cap.envelopes;
     int *spb = reinterpret_cast<int *>(val + (Lr + 1));       // SPCAP x 5
-    int *label = spb + SPCAP * 5;                            // 3 x SPCAP: available list, stack, cluster assignment
-    int *epc = label + 3 * SPCAP;                            // max(Lr, M) + 2
-    int *segbuf = epc + max(Lr, M) + 2;                      // per-trace segments, right-to-left: 64 x 4
+    int *label = spb + (int64_t)SPCAP * 5;                   // 3 x SPCAP: available list, stack, cluster assignment
+    int *epc = label + (int64_t)3 * SPCAP;                   // max(Lr, M) + 2
+    int *segbuf = epc + max(Lr, M) + 2;                      // per-trace segments, right-to-left: TRCAP x 4
+    int most_in_trace = 0;
     float *n2sc = p.n2sc + pw.row_off;
     forward_rows<true, true>(fm, res, Lr, sp, rowM, rowI, rowD, lane, xf, F, 0, nullptr);
     for (int pos = lane; pos <= Lr; pos += 32) acc[pos] = 0.0f;
@@ -294,7 +301,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) ensemble_kernel(EnsembleParams
             __syncwarp();
             // residues sqfrom+1 .. sqto get the ratio; sqfrom itself keeps 1.0 (as the reference does)
             for (int pos = sqfrom + 1 + lane; pos <= sqto; pos += 32) val[pos] = null2[res[pos - 1]];
-            if (lane == 0 && nseg < 64) { segbuf[nseg * 4 + 0] = sqfrom; segbuf[nseg * 4 + 1] = sqto; segbuf[nseg * 4 + 2] = hmmfrom; segbuf[nseg * 4 + 3] = hmmto; }
+            if (lane == 0 && nseg < TRCAP) { segbuf[nseg * 4 + 0] = sqfrom; segbuf[nseg * 4 + 1] = sqto; segbuf[nseg * 4 + 2] = hmmfrom; segbuf[nseg * 4 + 3] = hmmto; }
             nseg++;
             in_dom = false;
             __syncwarp();
@@ -308,18 +315,22 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) ensemble_kernel(EnsembleParams
       for (int pos = 1 + lane; pos <= Lr; pos += 32) acc[pos] += val[pos];
       // append this trace's segments left to right
       if (lane == 0) {
-        for (int z = min(nseg, 64) - 1; z >= 0; --z) {
+        most_in_trace = max(most_in_trace, nseg);
+        for (int z = min(nseg, TRCAP) - 1; z >= 0; --z) {
           if (nsp + 0 < SPCAP) {
             int *e = spb + nsp * 5;
             e[0] = t; e[1] = segbuf[z * 4 + 0] + reg.i - 1; e[2] = segbuf[z * 4 + 1] + reg.i - 1; e[3] = segbuf[z * 4 + 2]; e[4] = segbuf[z * 4 + 3];
           }
           nsp++;
         }
+        nsp += max(nseg - TRCAP, 0);        // segments the trace buffer had no room for still count towards what is needed
       }
       nsp = __shfl_sync(0xffffffffu, nsp, 0);
       __syncwarp();
     }
-    const bool sp_overflow = nsp > SPCAP;          // more sampled segments than the clustering buffers hold
+    most_in_trace = __shfl_sync(0xffffffffu, most_in_trace, 0);
+    const int nsp_all = nsp + 0;
+    const bool sp_overflow = nsp > SPCAP || most_in_trace > TRCAP;    // more sampled segments than the buffers hold
     nsp = min(nsp, SPCAP);
     for (int pos = reg.i + lane; pos <= reg.j; pos += 32) n2sc[pos] = (float)log((double)__fdiv_rn(acc[pos - reg.i + 1], (float)NSAMPLES));
     // ---- single-linkage clustering, numbering the clusters exactly as the sequential reference does: seed = last
@@ -359,7 +370,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) ensemble_kernel(EnsembleParams
     // ---- significant clusters -> envelopes (lane 0; the lists are short) ----
     if (lane == 0) {
       int nout = 0;
-      Envelope *eo = ep.env_out + (int64_t)ri * MAXENV;
+      Envelope *eo = ep.env_out + ep.env_off[ri];
       for (int c = 0; c < nc; ++c) {
         int idx_of_last = -1, ninc = 0;
         for (int h = 0; h < nsp; ++h) if (assign[h] == c) { if (spb[h * 5] != idx_of_last) ninc++; idx_of_last = spb[h * 5]; }
@@ -378,13 +389,14 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) ensemble_kernel(EnsembleParams
         for (cmv = 0, best_j = jmax; best_j >= jmin; --best_j) { cmv += epc[best_j - jmin]; if ((float)cmv / (float)ninc >= 0.02f) break; }
         if (best_i > best_j) continue;
         if (nout < MAXENV) { eo[nout].pair = reg.pair; eo[nout].i = best_i; eo[nout].j = best_j; eo[nout].null2_done = 1; eo[nout].scratch_off = 0; eo[nout].slot = 0; eo[nout].pad = 0; }
-        nout++;                          // counted past MAXENV: the host refuses the search rather than drop envelopes silently
+        nout++;                          // counted past MAXENV: the host repeats the region with room for all of them
       }
       const int nsig = nout;
       nout = min(nout, MAXENV);
       // order of occurrence in the target
       for (int a = 1; a < nout; ++a) { Envelope v = eo[a]; int b = a - 1; while (b >= 0 && eo[b].i > v.i) { eo[b + 1] = eo[b]; --b; } eo[b + 1] = v; }
-      ep.env_count[ri] = sp_overflow ? -1 : nsig;
+      ep.env_count[ri] = (sp_overflow || nsig > MAXENV) ? -1 : nsig;
+      ep.need[ri * 3 + 0] = nsp_all; ep.need[ri * 3 + 1] = most_in_trace; ep.need[ri * 3 + 2] = nsig;
     }
     __syncwarp();
   }
@@ -393,67 +405,87 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) ensemble_kernel(EnsembleParams
 // The ensemble of all multi-domain regions as an asynchronous job on stream `st`: ensembles_launch enqueues the uploads,
 // the kernel and the downloads; ensembles_collect waits for them and hands back the envelopes of every region.
 struct EnsembleJob {
-  DevBuf b_regs, b_idx, b_off, b_scr, b_env, b_cnt;       // workspaces from the engine's cache (the caller holds the PoolScope)
-  std::vector<int64_t> off;
+  DevBuf b_regs, b_idx, b_off, b_scr, b_env, b_cnt, b_caps, b_eoff, b_need;       // workspaces from the engine's cache (the caller holds the PoolScope)
+  std::vector<int64_t> off, env_off;
   std::vector<Envelope> envs;
-  std::vector<int32_t> cnt;
+  std::vector<int32_t> cnt, need;
+  std::vector<EnsembleCaps> caps;
   int nm = 0;
 };
 
 int ensembles_launch(ckm_engine *e, const ckm_models *m, DomdefParams &p, const std::vector<PairWork> &pairs,
-                     const std::vector<Region> &regs, const std::vector<int> &multi_idx, cudaStream_t st, EnsembleJob **job_out) {
+                     const std::vector<Region> &regs, const std::vector<int> &multi_idx, const std::vector<EnsembleCaps> &caps,
+                     cudaStream_t st, EnsembleJob **job_out) {
   EnsembleJob *job = new EnsembleJob();
   *job_out = job;
   const int nm = job->nm = (int)multi_idx.size();
-  job->off.resize(nm);
-  int64_t tot = 0;
+  job->off.resize(nm); job->env_off.resize(nm); job->caps = caps;
+  int64_t tot = 0, nenv = 0;
   for (int i = 0; i < nm; ++i) {
     const Region &r = regs[multi_idx[i]];
     const int64_t Lr = r.j - r.i + 1, M = m->models[pairs[r.pair].model].M, Mpad = ((M + 1) + 31) / 32 * 32 + 32;
     job->off[i] = tot;
-    tot += (Lr + 1) * 3 * Mpad + (Lr + 1) * X_NX + 2 * (Lr + 1) + (int64_t)SPCAP * 8 + std::max(Lr, M) + 2 + 256 + 64;
+    tot += (Lr + 1) * 3 * Mpad + (Lr + 1) * X_NX + 2 * (Lr + 1) + (int64_t)caps[i].segments * 8 + std::max(Lr, M) + 2 + (int64_t)caps[i].trace_segments * 4 + 64;
     tot = (tot + 63) / 64 * 64;
+    job->env_off[i] = nenv;
+    nenv += caps[i].envelopes;
   }
   int rc;
   if ((rc = job->b_regs.alloc(sizeof(Region) * regs.size())) || (rc = job->b_idx.alloc(sizeof(int32_t) * nm)) || (rc = job->b_off.alloc(sizeof(int64_t) * nm)) ||
-      (rc = job->b_scr.alloc(sizeof(float) * (size_t)tot)) || (rc = job->b_env.alloc(sizeof(Envelope) * (size_t)nm * MAXENV)) || (rc = job->b_cnt.alloc(sizeof(int32_t) * nm))) return rc;
+      (rc = job->b_scr.alloc(sizeof(float) * (size_t)tot)) || (rc = job->b_env.alloc(sizeof(Envelope) * (size_t)nenv)) || (rc = job->b_cnt.alloc(sizeof(int32_t) * nm)) ||
+      (rc = job->b_caps.alloc(sizeof(EnsembleCaps) * nm)) || (rc = job->b_eoff.alloc(sizeof(int64_t) * nm)) || (rc = job->b_need.alloc(sizeof(int32_t) * 3 * nm))) return rc;
   CKM_CUDA(cudaMemcpyAsync(job->b_regs.p, regs.data(), sizeof(Region) * regs.size(), cudaMemcpyHostToDevice, st));       // regs, multi_idx outlive the job (caller)
   CKM_CUDA(cudaMemcpyAsync(job->b_idx.p, multi_idx.data(), sizeof(int32_t) * nm, cudaMemcpyHostToDevice, st));
   CKM_CUDA(cudaMemcpyAsync(job->b_off.p, job->off.data(), sizeof(int64_t) * nm, cudaMemcpyHostToDevice, st));
+  CKM_CUDA(cudaMemcpyAsync(job->b_caps.p, job->caps.data(), sizeof(EnsembleCaps) * nm, cudaMemcpyHostToDevice, st));
+  CKM_CUDA(cudaMemcpyAsync(job->b_eoff.p, job->env_off.data(), sizeof(int64_t) * nm, cudaMemcpyHostToDevice, st));
   CKM_CUDA(cudaMemsetAsync(job->b_cnt.p, 0, sizeof(int32_t) * nm, st));
-  CKM_CUDA(cudaMemsetAsync(job->b_env.p, 0, sizeof(Envelope) * (size_t)nm * MAXENV, st));      // the kernel fills only the slots it uses; the whole block is copied back
+  CKM_CUDA(cudaMemsetAsync(job->b_need.p, 0, sizeof(int32_t) * 3 * nm, st));
+  CKM_CUDA(cudaMemsetAsync(job->b_env.p, 0, sizeof(Envelope) * (size_t)nenv, st));      // the kernel fills only the slots it uses; the whole block is copied back
   EnsembleParams ep;
   ep.d = p; ep.regions = job->b_regs.as<Region>(); ep.multi_idx = job->b_idx.as<int32_t>(); ep.nmulti = nm;
   ep.scratch_off = job->b_off.as<int64_t>(); ep.scratch = job->b_scr.as<float>(); ep.env_out = job->b_env.as<Envelope>(); ep.env_count = job->b_cnt.as<int32_t>();
+  ep.caps = job->b_caps.as<EnsembleCaps>(); ep.env_off = job->b_eoff.as<int64_t>(); ep.need = job->b_need.as<int32_t>();
   const size_t smem = (size_t)FWD_WARPS * 3 * p.row_elems * sizeof(float);
   CKM_CUDA(cudaFuncSetAttribute(ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(e->prop.multiProcessorCount * 4, (nm + FWD_WARPS - 1) / FWD_WARPS);
   ensemble_kernel<<<grid, FWD_WARPS * 32, smem, st>>>(ep);
   CKM_CUDA(cudaGetLastError());
   e->stats.kernel_launches++;
-  job->envs.resize((size_t)nm * MAXENV);
-  job->cnt.resize(nm);
+  job->envs.resize((size_t)nenv);
+  job->cnt.resize(nm); job->need.resize((size_t)3 * nm);
   CKM_CUDA(cudaMemcpyAsync(job->envs.data(), job->b_env.p, sizeof(Envelope) * job->envs.size(), cudaMemcpyDeviceToHost, st));
   CKM_CUDA(cudaMemcpyAsync(job->cnt.data(), job->b_cnt.p, sizeof(int32_t) * nm, cudaMemcpyDeviceToHost, st));
+  CKM_CUDA(cudaMemcpyAsync(job->need.data(), job->b_need.p, sizeof(int32_t) * 3 * nm, cudaMemcpyDeviceToHost, st));
   return CKM_OK;
 }
 
-int ensembles_collect(EnsembleJob *job, cudaStream_t st, std::vector<std::vector<Envelope>> &out) {
+// out[i]: the envelopes of multi region i.  grow[i]: empty capacities (all zero) when the region fitted, else what it needs:
+// the caller repeats the domain phase with them (hmmsearch reports every domain, so must this).
+int ensembles_collect(EnsembleJob *job, cudaStream_t st, std::vector<std::vector<Envelope>> &out, std::vector<EnsembleCaps> &grow, int *n_over) {
   cudaError_t err = cudaStreamSynchronize(st);
-  int over = 0;
+  *n_over = 0;
   if (err == cudaSuccess) {
     out.assign((size_t)job->nm, {});
+    grow.assign((size_t)job->nm, EnsembleCaps{0, 0, 0});
     for (int i = 0; i < job->nm; ++i) {
-      if (job->cnt[i] < 0 || job->cnt[i] > MAXENV) { over++; continue; }
-      for (int c = 0; c < job->cnt[i]; ++c) out[i].push_back(job->envs[(size_t)i * MAXENV + c]);
+      if (job->cnt[i] < 0) {
+        const EnsembleCaps &c = job->caps[i];
+        const bool traces_cut = job->need[3 * i] > c.segments || job->need[3 * i + 1] > c.trace_segments;
+        EnsembleCaps g = c;
+        g.segments = std::max(c.segments, job->need[3 * i] + 64);
+        g.trace_segments = std::max(c.trace_segments, job->need[3 * i + 1] + 8);
+        // with the segment list cut short the cluster count is only a lower bound: leave room, the next pass knows exactly
+        g.envelopes = std::max(c.envelopes, traces_cut ? std::max(2 * job->need[3 * i + 2], job->need[3 * i + 1] + 8) : job->need[3 * i + 2]);
+        grow[i] = g;
+        ++*n_over;
+        continue;
+      }
+      for (int c = 0; c < job->cnt[i]; ++c) out[i].push_back(job->envs[(size_t)job->env_off[i] + c]);
     }
   }
   delete job;
   if (err != cudaSuccess) return cuda_fail(err, "ensemble job");
-  if (over) {      // hmmsearch would report every domain; refusing is better than a shorter table
-    set_error("a multi-domain region resolves into more than 32 domains (or 4096 sampled segments): beyond the engine's per-region capacity");
-    return CKM_ECAPACITY;
-  }
   return CKM_OK;
 }
 void ensembles_abandon(EnsembleJob *job, cudaStream_t st) { if (job) { cudaStreamSynchronize(st); delete job; } }

@@ -298,8 +298,9 @@ namespace ckm {
 constexpr int X_NX_HOST = 6;
 struct EnsembleJob;
 int ensembles_launch(ckm_engine *e, const ckm_models *m, DomdefParams &p, const std::vector<PairWork> &pairs,
-                     const std::vector<Region> &regs, const std::vector<int> &multi_idx, cudaStream_t st, EnsembleJob **job_out);
-int ensembles_collect(EnsembleJob *job, cudaStream_t st, std::vector<std::vector<Envelope>> &out);
+                     const std::vector<Region> &regs, const std::vector<int> &multi_idx, const std::vector<EnsembleCaps> &caps,
+                     cudaStream_t st, EnsembleJob **job_out);
+int ensembles_collect(EnsembleJob *job, cudaStream_t st, std::vector<std::vector<Envelope>> &out, std::vector<EnsembleCaps> &grow, int *n_over);
 void ensembles_abandon(EnsembleJob *job, cudaStream_t st);
 
 static bool use_blocked_kernels() { const char *v = std::getenv("CKM_BLK"); return !(v != nullptr && v[0] == '0'); }
@@ -546,22 +547,27 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
     // per single-domain region, ENS_MAXENV per multi-domain region (the ensemble decides how many it fills; unused slots
     // keep ok = 0 and are skipped by every consumer).  Fixing the slots before the ensemble has run lets the envelopes of
     // the single-domain regions be rescored WHILE the trace ensemble of the multi-domain ones is still sampling.
+    // A region that turns out to hold more domains than its slots (or more sampled segments than its clustering buffers)
+    // reports what it needs, and the phase is repeated from here with that region's capacities raised.
     std::vector<int> multi_idx;
+    for (int r = 0; r < nreg; ++r) if (regs[r].multi) multi_idx.push_back(r);
+    std::vector<EnsembleCaps> caps(multi_idx.size(), ENS_DEFAULT_CAPS);
     std::vector<int32_t> reg_slot((size_t)nreg);
+    DevBuf denvs2, deorder2;
+    for (int pass = 0;; ++pass) {
     int32_t nslots = 0;
-    for (int r = 0; r < nreg; ++r) {
+    for (auto &pw : pairs) { pw.ndom_slots = 0; pw.first_dom = 0; }
+    for (int r = 0, mi = 0; r < nreg; ++r) {
       PairWork &pw = pairs[regs[r].pair];
       if (pw.ndom_slots == 0) pw.first_dom = nslots;
       reg_slot[r] = nslots;
-      const int k = regs[r].multi ? ENS_MAXENV : 1;
+      const int k = regs[r].multi ? caps[mi++].envelopes : 1;
       nslots += k; pw.ndom_slots += k;
-      if (regs[r].multi) multi_idx.push_back(r);
     }
     doms.assign((size_t)nslots, DomainOut{});
     std::vector<Envelope> envs1, envs2;
     for (int r = 0; r < nreg; ++r)
       if (!regs[r].multi) { Envelope en{}; en.pair = regs[r].pair; en.i = regs[r].i; en.j = regs[r].j; en.slot = reg_slot[r]; envs1.push_back(en); }
-    DevBuf denvs2, deorder2;
     if (nslots > 0) {
       if ((rc = ddoms.alloc(sizeof(DomainOut) * (size_t)nslots)) || (rc = dhits.alloc(sizeof(HitOut) * pairs.size()))) return rc;
       CKM_CUDA(cudaMemsetAsync(ddoms.p, 0, sizeof(DomainOut) * (size_t)nslots, st));
@@ -578,16 +584,24 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
       if (!multi_idx.empty()) {
         CKM_CUDA(cudaEventRecord(e->fan_ev, st));
         CKM_CUDA(cudaStreamWaitEvent(e->aux, e->fan_ev, 0));
-        if ((rc = ensembles_launch(e, m, p, pairs, regs, multi_idx, e->aux, &job))) { ensembles_abandon(job, e->aux); return rc; }
+        if ((rc = ensembles_launch(e, m, p, pairs, regs, multi_idx, caps, e->aux, &job))) { ensembles_abandon(job, e->aux); return rc; }
         if (!envs1.empty()) { if ((rc = fan_in(e))) { ensembles_abandon(job, e->aux); return rc; } CKM_CUDA(cudaStreamSynchronize(st)); }
       }
       if (job != nullptr) {
         std::vector<std::vector<Envelope>> multi_envs;
-        if ((rc = ensembles_collect(job, e->aux, multi_envs))) return rc;
+        std::vector<EnsembleCaps> grow;
+        int n_over = 0;
+        if ((rc = ensembles_collect(job, e->aux, multi_envs, grow, &n_over))) return rc;
         tr.mark("batch 1 + ensemble done");
+        if (n_over > 0) {
+          if (pass >= 3) { set_error("a multi-domain region keeps outgrowing the capacities it asked for"); return CKM_ECAPACITY; }
+          for (size_t mi = 0; mi < caps.size(); ++mi) if (grow[mi].segments) caps[mi] = grow[mi];
+          e->stats.n_queue_retries++;
+          continue;
+        }
         for (size_t mi = 0; mi < multi_idx.size(); ++mi) {
           int c = 0;
-          for (Envelope en : multi_envs[mi]) { en.slot = reg_slot[multi_idx[mi]] + c++; envs2.push_back(en); }     // at most ENS_MAXENV (ensembles_collect refuses more)
+          for (Envelope en : multi_envs[mi]) { en.slot = reg_slot[multi_idx[mi]] + c++; envs2.push_back(en); }     // no more than the region's slots (ensembles_collect)
         }
         if ((rc = run_env_batch(envs2, denvs2, deorder2, false))) return rc;
         tr.mark("envelope batch 2 done");
@@ -601,6 +615,8 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
     } else {
       for (auto &h : hout) std::memset(&h, 0, sizeof(h));
     }
+    break;
+    }   // pass
   }
   CKM_CUDA(cudaEventRecord(e->ev[7], st));
   CKM_CUDA(cudaEventSynchronize(e->ev[7]));

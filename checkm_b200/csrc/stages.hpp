@@ -98,7 +98,10 @@ struct PairWork {          // one pair that passed the Forward filter
   int64_t row_off;                   // offset (in rows of L+1) of its per-residue arrays
 };
 struct Region { int32_t pair, i, j, multi; };
-constexpr int ENS_MAXENV = 32;      // envelopes (= domain slots) a multi-domain region can yield
+constexpr int ENS_MAXENV = 32;      // envelopes (= domain slots) a multi-domain region can yield before its capacities are raised
+// capacities of one multi-domain region in the trace ensemble (kernels_ensemble.cu); the defaults, raised on demand
+struct EnsembleCaps { int32_t segments, trace_segments, envelopes; };
+constexpr EnsembleCaps ENS_DEFAULT_CAPS = {4096, 64, ENS_MAXENV};
 struct Envelope { int32_t pair, i, j, null2_done; int64_t scratch_off; int32_t slot, pad; };   // slot: index of its DomainOut
 struct DomainOut {
   int32_t pair, ienv, jenv, hmmfrom, hmmto, sqfrom, sqto, ok;

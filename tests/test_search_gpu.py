@@ -186,3 +186,31 @@ def test_search_giant_and_tiny_sequences(engine, cpr_models, cpr_oracle, oracle)
     on_giant = [r for r in rows if r['seqidx'] == 40]
     assert len(on_giant) >= 20, len(on_giant)
     print('giant sequence: %d domain rows of %d families; worst score diff %g' % (len(on_giant), len({r['model'] for r in on_giant}), compare(rows, hits)))
+
+
+def test_region_with_more_domains_than_slots(engine, cpr_models, cpr_oracle, oracle):
+    """150 internal fragments of a 57-position family back to back: two regions of ambiguous boundaries that the trace ensemble
+    resolves into 150 domains -- more than the 32 slots, the 4,096 sampled segments and the 64 segments per trace a region
+    starts with.  The regions report what they need and the domain phase is repeated; the table equals the oracle's, which
+    has no such limits."""
+    hm = synth.read_hmms(CPR_HMM)
+    fam = min(hm, key=lambda h: h.M)
+    rng = np.random.default_rng(103)
+    repeats = np.concatenate([synth.emit_homolog(fam, rng, k_from=int(rng.integers(20, 25)), k_to=int(rng.integers(45, 50)), sharpen=0.6)
+                              for _ in range(150)])
+    b = synth.make_bin('r', hm, seed=78, n_orfs=120, max_len=900)
+    seqs = [b.seq(i) for i in range(15)] + [repeats] + [b.seq(i) for i in range(15, 30)]
+    residues = np.concatenate(seqs)
+    offsets = np.concatenate([[0], np.cumsum([len(s) for s in seqs])]).astype(np.int64)
+    db = engine.seqdb(residues, offsets)
+    hits = engine.search(cpr_models, db)
+    st = engine.stats()
+    db.close()
+    rp = oracle.search(cpr_oracle, residues, offsets, nthreads=8)
+    rows = oracle.hits_table(rp)
+    regions = [(rp.contents.hits[h].nregions, rp.contents.hits[h].nclustered, rp.contents.hits[h].nenvelopes) for h in range(rp.contents.nhits)
+               if rp.contents.hits[h].nenvelopes > 64]
+    oracle.free_results(rp)
+    print('repeat protein (regions, clustered, envelopes):', regions, 'passes repeated:', st.n_queue_retries, 'worst score diff', compare(rows, hits))
+    assert regions and regions[0][2] > 64 * regions[0][0] // 2
+    assert st.n_queue_retries >= 1
