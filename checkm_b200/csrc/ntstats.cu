@@ -377,8 +377,7 @@ int ckm_scaffold_stats(ckm_engine *e, const uint8_t *bytes, int64_t nbytes, cons
   p.contig_scaf = dcs.as<uint32_t>(); p.contig_len = dcl.as<uint32_t>();
   p.ncontigs = reinterpret_cast<unsigned long long *>(dctr.as<uint8_t>() + 8); p.cap = contig_cap;
   const int dyn_smem = NT_WARPS * NT_WARP_SMEM;
-  static bool attr_set = false;
-  if (!attr_set) { CKM_CUDA(cudaFuncSetAttribute(ntstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem)); attr_set = true; }
+  CKM_CUDA(cudaFuncSetAttribute(ntstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
   CKM_CUDA(cudaEventRecord(e->ev[0], st));
   ntstats_kernel<<<grid, NT_THREADS, dyn_smem, st>>>(p);
   CKM_CUDA(cudaGetLastError());
