@@ -281,6 +281,7 @@ int ckm_fasta_scan_nt(const char *text, int64_t n, uint8_t *bytes_out, int64_t b
     set_error("ckm_fasta_scan_nt: bad argument"); return CKM_EINVAL;
   }
   int32_t nrec = 0; int64_t used = 0, hb = 0, i = 0;
+  const bool has_cr = n > 0 && std::memchr(text, '\r', (size_t)n) != nullptr;      // files without one skip the per-line search
   auto close_record = [&]() {
     if (nrec == 0) return;
     const int64_t end = starts_out[nrec - 1] + lens_out[nrec - 1];
@@ -291,7 +292,7 @@ int ckm_fasta_scan_nt(const char *text, int64_t n, uint8_t *bytes_out, int64_t b
   while (i < n) {
     const char *nl = (const char *)std::memchr(text + i, '\n', (size_t)(n - i));
     int64_t e = nl ? (nl - text) : n;                           // candidate line [i, e), terminator at e (or none)
-    const char *cr = (const char *)std::memchr(text + i, '\r', (size_t)(e - i));
+    const char *cr = has_cr ? (const char *)std::memchr(text + i, '\r', (size_t)(e - i)) : nullptr;
     int64_t next = e + 1; bool terminated = nl != nullptr;
     if (cr) { e = cr - text; terminated = true; next = (e + 1 < n && text[e + 1] == '\n') ? e + 2 : e + 1; }
     bool blank = true;

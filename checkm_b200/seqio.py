@@ -20,7 +20,7 @@ def read_fasta(path):
 
 def parse_fasta(raw):
     n = len(raw)
-    max_rec = raw.count(b'>')
+    max_rec = int(np.count_nonzero(np.frombuffer(raw, dtype=np.uint8) == 62))     # '>' bytes: an upper bound on the records
     residues = np.empty(max(n, 1), dtype=np.uint8)
     offsets = np.zeros(max_rec + 1, dtype=np.int64)
     headers = C.create_string_buffer(max(n, 1))
@@ -48,7 +48,7 @@ def scan_nt_fasta(raw):
     device scan: returns ids (first token of each header line), the byte buffer, and the start (a multiple of 64) and
     length of every record.  A record whose id repeats replaces the earlier one, as in the reference's dict."""
     n = len(raw)
-    max_rec = raw.count(b'>')
+    max_rec = int(np.count_nonzero(np.frombuffer(raw, dtype=np.uint8) == 62))     # '>' bytes: an upper bound on the records
     data = np.empty(n + 64 * (max_rec + 1), dtype=np.uint8)
     starts = np.zeros(max(max_rec, 1), dtype=np.int64)
     lens = np.zeros(max(max_rec, 1), dtype=np.int64)
