@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-end check on one B200: GPU tests, smoke, default bench + reference arm, launch list of the default command, configs 4 / 2, diverse db
+# round-end check on one B200: GPU tests, smoke, default bench + reference arm, launch list of the default command, configs 4 / 2, diverse db, bin-statistics scan
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 ( time python -m pytest tests -m gpu -q ) > gpurun_out/r2_t9.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2_t9.log
@@ -10,6 +10,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ( time python bench.py --config 4 --steps 2 --warmup 1 --no-cpu-baseline ) > gpurun_out/r2_b9_c4.log 2>&1
 ( time python bench.py --db diverse --steps 3 --warmup 2 --no-plugin --no-cpu-baseline ) > gpurun_out/r2_b9_div.log 2>&1
 ( time python bench.py --config 2 --steps 2 --warmup 1 --bins-per-step 25 ) > gpurun_out/r2_b9_c2.log 2>&1
+( time python tools/bench_binstats.py --bins 1000 ) > gpurun_out/r2_binstats_1000.json 2> gpurun_out/r2_binstats.err; echo "binstats rc=$?"; cut -c1-200 gpurun_out/r2_binstats_1000.json
 python - <<'PY'
 import json
 for f in ('r2_b9','r2_b9_ref','r2_b9_c4','r2_b9_div','r2_b9_c2'):
