@@ -5,8 +5,8 @@ import os
 import sys
 
 try:                                              # inside a CheckM install: CheckM's own helpers
-    from checkm.common import (checkFileExists, makeSurePathExists, binIdFromFilename,       # noqa: F401
-                               reassignStdOut, restoreStdOut)
+    from checkm.common import (checkFileExists, checkDirExists, makeSurePathExists, binIdFromFilename,       # noqa: F401
+                               getBinIdsFromOutDir, reassignStdOut, restoreStdOut)
 except Exception:                                 # stand-alone
     def _fatal(message):
         logging.getLogger('timestamp').error(message + '\n')
@@ -16,6 +16,16 @@ except Exception:                                 # stand-alone
         if os.path.exists(inputFile):
             return
         _fatal('Input file does not exists: ' + inputFile)
+
+    def checkDirExists(inputDir):
+        if os.path.exists(inputDir):
+            return
+        _fatal('Input directory does not exists: ' + inputDir)
+
+    def getBinIdsFromOutDir(outDir):
+        """Sub-directories of <outDir>/bins, in directory order (what the reference iterates over)."""
+        binDir = os.path.join(outDir, 'bins')
+        return [f for f in os.listdir(binDir) if f != 'storage' and os.path.isdir(os.path.join(binDir, f))]
 
     def makeSurePathExists(path):
         if path:

@@ -33,6 +33,10 @@ class DefaultValues(object):
     PFAM_CLAN_FILE = os.path.join(CHECKM_DATA_DIR, 'pfam', 'Pfam-A.hmm.dat')
     SELECTED_MARKER_SETS = os.path.join(CHECKM_DATA_DIR, 'selected_marker_sets.tsv')
     TAXON_MARKER_SETS = os.path.join(CHECKM_DATA_DIR, 'taxon_marker_sets.tsv')
+    GENOME_TREE_DIR = os.path.join(CHECKM_DATA_DIR, 'genome_tree')                      # defaultValues.py:60-70
+    GENOME_TREE_METADATA = 'genome_tree.metadata.tsv'
+    GENOME_TREE_MISSING_DUPLICATE = 'missing_duplicate_genes_50.tsv'
+    PPLACER_TREE_OUT = 'concatenated.tre'                                               # defaultValues.py:89
 
     PHYLO_HMM_MODEL_INFO = 'phylo_hmm_info.pkl.gz'
     CHECKM_HMM_MODEL_INFO = 'checkm_hmm_info.pkl.gz'
@@ -58,3 +62,4 @@ class DefaultValues(object):
         cls.PFAM_CLAN_FILE = os.path.join(root, 'pfam', 'Pfam-A.hmm.dat')
         cls.SELECTED_MARKER_SETS = os.path.join(root, 'selected_marker_sets.tsv')
         cls.TAXON_MARKER_SETS = os.path.join(root, 'taxon_marker_sets.tsv')
+        cls.GENOME_TREE_DIR = os.path.join(root, 'genome_tree')

@@ -233,3 +233,65 @@ def test_find_with_an_empty_gene_file(dataroot, tmp_path):
         ms = MarkerSetParser(1).getMarkerSets(out, ids, CPR_HMM)
         assert RP.results['nothing'].markerHits == {}
         assert RP.results['nothing'].geneCountsForSelectedMarkerSet(ms['nothing'], False) == [43, 0, 0, 0, 0, 0, 0.0, 0.0]
+
+
+def test_lineage_wf_in_miniature(dataroot, tmp_path):
+    """`checkm lineage_wf` minus Prodigal and pplacer (BASELINE.json configs[2]'s workflow):
+    tree search (main.py:181-222) -> reduction -> TreeParser.getBinMarkerSets on the placed tree (treeParser.py:468-553) ->
+    find with the lineage marker file it wrote (per-bin subsets) -> qa.  Expected values: tests/golden/lineage/expected.json['wf'],
+    every selection / reduction / report step of which is the REFERENCE's code (tests/golden/make_lineage_goldens.py)."""
+    from checkm_b200.defaultValues import DefaultValues
+    from checkm_b200.markerGeneFinder import MarkerGeneFinder
+    from checkm_b200.markerSets import MarkerSetParser, _parse_set_list
+    from checkm_b200.resultsParser import ResultsParser
+    from checkm_b200.treeParser import TreeParser
+    lin = os.path.join(GOLDEN, 'lineage')
+    with open(os.path.join(lin, 'expected.json')) as f:
+        exp = json.load(f)['wf']
+    # the data root of the e2e tests plus the genome-tree metadata
+    shutil.copytree(os.path.join(lin, 'data', 'genome_tree'), os.path.join(dataroot, 'genome_tree'), dirs_exist_ok=True)
+    saved_selected = open(DefaultValues.SELECTED_MARKER_SETS).read()
+    shutil.copyfile(os.path.join(lin, 'data', 'selected_marker_sets.tsv'), DefaultValues.SELECTED_MARKER_SETS)
+    try:
+        out = str(tmp_path / 'out')
+        os.makedirs(os.path.join(out, 'storage', 'tree'))
+        shutil.copyfile(os.path.join(lin, 'tree', 'concatenated.tre'), os.path.join(out, 'storage', 'tree', 'concatenated.tre'))
+        # ---- tree: the phylogenetic markers (the 43 CPR models stand in for phylo.hmm) ----
+        phylo = MarkerGeneFinder(1).find(BINFILES, out, 'hmmer.tree.txt', 'hmmer.tree.ali.txt', CPR_HMM, False, False, True)
+        with open(os.path.join(out, 'storage', 'bin_stats.tree.tsv'), 'w') as f:
+            for i, binId in enumerate(BIN_IDS):
+                nseq = sum(1 for l in open(os.path.join(out, 'bins', binId, 'genes.faa')) if l.startswith('>'))
+                f.write(binId + '\t' + BIN_STATS % (0.41 + 0.07 * i, 180000 + 1111 * i, nseq) + '\n')
+        shutil.copyfile(os.path.join(out, 'storage', 'bin_stats.tree.tsv'), os.path.join(out, 'storage', 'bin_stats.analyze.tsv'))
+        # ---- lineage_set ----
+        RPt = ResultsParser(phylo)
+        RPt.analyseResults(out, 'bin_stats.tree.tsv', 'hmmer.tree.txt')
+        assert {b: list(RPt.results[b].countUniqueHits()) for b in BIN_IDS} == exp['unique_multi']
+        mf = os.path.join(out, 'lineage.ms')
+        TreeParser().getBinMarkerSets(out, mf, 2, 0, False, False, False, RPt, 10, 10)
+        got = {}
+        for line in list(open(mf))[1:]:
+            fields = line.rstrip('\n').split('\t')
+            got[fields[0]] = [[fields[2 + 4 * i], fields[3 + 4 * i], int(fields[4 + 4 * i]),
+                               [sorted(s) for s in _parse_set_list(fields[5 + 4 * i])]] for i in range(int(fields[1]))]
+        assert got == exp['marker_sets']
+        # ---- analyze + qa with the file just written ----
+        models = MarkerGeneFinder(1).find(BINFILES, out, 'hmmer.analyze.txt', 'hmmer.analyze.ali.txt', mf, False, False, True)
+        for binId in BIN_IDS:
+            assert list(models[binId].keys()) == exp['subset'][binId]
+            rows = _data_lines(os.path.join(out, 'bins', binId, 'hmmer.analyze.txt'))
+            assert [r.split() for r in rows] == [r.split() for r in exp['domtblout'][binId]], binId
+        bms = MarkerSetParser(1).getMarkerSets(out, BIN_IDS, mf)
+        RP = ResultsParser(models)
+        RP.analyseResults(out, 'bin_stats.analyze.tsv', 'hmmer.analyze.txt')
+        for b in BIN_IDS:
+            assert str(bms[b].selectedMarkerSet().UID) == exp['selected_uid'][b]
+            assert [repr(v) for v in RP.results[b].geneCountsForSelectedMarkerSet(bms[b], False)] == [repr(v) for v in exp['counts'][b]]
+        for fmt, want in exp['tables'].items():
+            buf = io.StringIO()
+            with redirect_stdout(buf):
+                RP.printSummary(int(fmt), _AAI(), bms, False, None, True, '', out)
+            assert buf.getvalue() == want, fmt
+    finally:
+        with open(DefaultValues.SELECTED_MARKER_SETS, 'w') as f:
+            f.write(saved_selected)
