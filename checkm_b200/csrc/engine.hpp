@@ -8,6 +8,9 @@
 #include "hmm_model.hpp"
 
 namespace ckm {
+// Longest model the engine takes.  The chunked fp32 kernels (M > 1024) keep three DP rows of ((M + 31) / 32 * 32 + 64) floats per
+// warp, four warps per CTA, in shared memory: 4 * 3 * 4 * (4608 + 64) = 224,256 of the 232,448 bytes a CTA may own.
+constexpr int MAX_MODEL_M = 4608;
 
 // ------------------------------------------------------------------------------------------------
 // SSV tiles.  A tile is what one warp sweeps down a sequence: 64 "slots" (lane l low half = slot l,
@@ -108,6 +111,8 @@ struct ckm_models {
   std::vector<ckm::TileGroup> groups;
   std::vector<int32_t>        chain_first_tile;   // per chain
   std::vector<int32_t>        chain_ntiles;
+  std::vector<int32_t>        ssv_bypass;         // models without SSV tiles (chain larger than shared memory): all their pairs are MSV candidates
+  int32_t        *d_ssv_bypass = nullptr;
   ckm::TileDesc  *d_tiles = nullptr;
   ckm::TileModel *d_tile_models = nullptr;
   ckm::TileGroup *d_groups = nullptr;

@@ -12,6 +12,7 @@
 // or (conservatively) the filter's pass threshold is re-scored by the exact byte-for-byte MSV kernel below; all
 // other pairs are provably rejected by the real filter.  No value ever has to be exact once it is past the bound,
 // so int16 wrap-around after thousands of rows is harmless (the maximum was recorded before the wrap).
+#include <algorithm>
 #include "engine.hpp"
 #include "device_utils.cuh"
 #include "stages.hpp"
@@ -507,6 +508,30 @@ int launch_msv2(const MsvParams &p, int cls, int grid, cudaStream_t stream) {
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? CKM_OK : cuda_fail(e, "msv2_kernel launch");
+}
+
+// Models too long for a chain of SSV tiles (models.cu: ssv_bypass) skip the pre-filter: all of their pairs become candidates.
+__global__ void ssv_bypass_kernel(const int32_t *models, int32_t nbypass, int32_t nseq, const int32_t *len, const int32_t *bin,
+                                  const uint8_t *model_active, int32_t nmodels_db, int2 *cand, int32_t *cand_count, int32_t cand_cap) {
+  const int64_t n = (int64_t)nbypass * nseq;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i % nseq), m = models[i / nseq];
+    if (len[s] == 0) continue;
+    if (model_active != nullptr && !model_active[(int64_t)bin[s] * nmodels_db + m]) continue;
+    const int pos = atomicAdd(cand_count, 1);
+    if (pos < cand_cap) cand[pos] = make_int2(s, m);
+  }
+}
+
+int launch_ssv_bypass(const int32_t *models, int32_t nbypass, int32_t nseq, const int32_t *len, const int32_t *bin,
+                      const uint8_t *model_active, int32_t nmodels_db, int2 *cand, int32_t *cand_count, int32_t cand_cap,
+                      cudaStream_t stream) {
+  if (nbypass <= 0 || nseq <= 0) return CKM_OK;
+  const int64_t n = (int64_t)nbypass * nseq;
+  const int grid = (int)std::min<int64_t>(1184, (n + 255) / 256);
+  ssv_bypass_kernel<<<grid, 256, 0, stream>>>(models, nbypass, nseq, len, bin, model_active, nmodels_db, cand, cand_count, cand_cap);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? CKM_OK : cuda_fail(e, "ssv_bypass_kernel launch");
 }
 
 int launch_msv_exact(const MsvParams &p, int grid, cudaStream_t stream) {

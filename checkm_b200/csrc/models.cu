@@ -71,9 +71,14 @@ static void build_tiles(ckm_models &db, std::vector<uint8_t> &blob) {
     for (size_t t = first; t < tiles.size(); ++t) chains.push_back({(int)t, 1});
   }
   const int chunk_cells = 64 * chainJ;
+  const int64_t cap = 200000;                 // shared-memory budget of one tile group
+  db.ssv_bypass.clear();
   for (const Item &it : longm) {
     int ncells = it.M + 1;                    // real cells + the mandatory padding cell
     int nch = (ncells + chunk_cells - 1) / chunk_cells;
+    // All chunks of a chain sit in shared memory together.  A model whose chain does not fit (M >= 3072) gets no tiles:
+    // every pair of it goes straight to the exact MSV kernel (ssv_bypass_kernel), which has no such limit.
+    if ((int64_t)nch * tile_block_bytes_host(chainJ) > cap) { db.ssv_bypass.push_back(it.model); continue; }
     chains.push_back({(int)tiles.size(), nch});
     for (int c = 0; c < nch; ++c) {
       HostTile ht{chainJ, {}, 64, c > 0, c + 1 < nch};
@@ -83,7 +88,6 @@ static void build_tiles(ckm_models &db, std::vector<uint8_t> &blob) {
     }
   }
   // groups: consecutive chains of equal J up to the shared-memory budget
-  const int64_t cap = 200000;
   db.tiles.clear(); db.tile_models.clear(); db.groups.clear(); db.chain_first_tile.clear(); db.chain_ntiles.clear();
   int64_t off = 0;
   for (size_t t = 0; t < tiles.size(); ++t) {
@@ -191,6 +195,10 @@ int models_build_device(ckm_models &db) {
     s.msv2_ok = (s.vq != 0 && (int)m.base_b + (int)m.bias_b < 255) ? 1 : 0;
     blk_units += s.vq;
     db.maxM = std::max(db.maxM, m.M);
+    if (m.M > MAX_MODEL_M) {
+      set_error("model " + m.name + " has " + std::to_string(m.M) + " positions; the engine's DP rows hold at most " + std::to_string(MAX_MODEL_M));
+      return CKM_EINVAL;
+    }
   }
   if (cols > (int64_t)1 << 30) { set_error("model database too large"); return CKM_ENOMEM; }
   db.total_cols = cols;
@@ -303,13 +311,14 @@ int models_build_device(ckm_models &db) {
   if ((st = upload(&db.d_groups, db.groups))) return st;
   if ((st = upload(&db.d_chain_first_tile, db.chain_first_tile))) return st;
   if ((st = upload(&db.d_chain_ntiles, db.chain_ntiles))) return st;
+  if ((st = upload(&db.d_ssv_bypass, db.ssv_bypass))) return st;
   return CKM_OK;
 }
 
 void models_free_device(ckm_models &db) {
   cudaFree(db.d_scalars); cudaFree(db.d_rbv); cudaFree(db.d_rwv); cudaFree(db.d_twv); cudaFree(db.d_rfv); cudaFree(db.d_tfv);
   cudaFree(db.d_bias_eo); cudaFree(db.d_twb); cudaFree(db.d_twp); cudaFree(db.d_rwp); cudaFree(db.d_rwb); cudaFree(db.d_rmb); cudaFree(db.d_tfb); cudaFree(db.d_rfb); cudaFree(db.d_tile_blob); cudaFree(db.d_tiles); cudaFree(db.d_tile_models); cudaFree(db.d_groups);
-  cudaFree(db.d_chain_first_tile); cudaFree(db.d_chain_ntiles);
+  cudaFree(db.d_chain_first_tile); cudaFree(db.d_chain_ntiles); cudaFree(db.d_ssv_bypass);
 }
 
 }  // namespace ckm

@@ -98,6 +98,8 @@ static int run_stage1(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
   cudaStream_t st = e->stream;
   int rc;
   s1.cand_cap = queue_cap(n_pairs, 6, attempt);
+  const int64_t n_bypass = (int64_t)m->ssv_bypass.size() * db->nseq;          // models without SSV tiles: every pair is a candidate
+  s1.cand_cap = (int32_t)std::min<int64_t>(QUEUE_MAX, (int64_t)s1.cand_cap + n_bypass);
   s1.pass_cap = queue_cap(n_pairs, 12, attempt);
   if ((rc = s1.cand.alloc(sizeof(int2) * (size_t)s1.cand_cap))) return rc;
   if ((rc = s1.pass.alloc(sizeof(Candidate) * (size_t)s1.pass_cap))) return rc;
@@ -151,6 +153,12 @@ static int run_stage1(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
     const int64_t units = (int64_t)p.ngroups * p.nchunks;
     const int grid = (int)std::min<int64_t>(nsm, units);
     if ((rc = launch_ssv(Js[c], p, grid, (size_t)maxbytes, st))) return rc;
+    e->stats.kernel_launches++;
+  }
+  if (!m->ssv_bypass.empty()) {
+    if ((rc = launch_ssv_bypass(m->d_ssv_bypass, (int32_t)m->ssv_bypass.size(), db->nseq, db->d_len, db->d_bin,
+                                am.all_active ? nullptr : am.model_active.as<uint8_t>(), (int32_t)m->models.size(),
+                                s1.cand.as<int2>(), e->d_counters + CTR_CAND, s1.cand_cap, st))) return rc;
     e->stats.kernel_launches++;
   }
   CKM_CUDA(cudaEventRecord(e->ev[1], st));

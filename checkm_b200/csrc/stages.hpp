@@ -56,6 +56,10 @@ struct MsvParams {
 };
 
 int launch_msv_exact(const MsvParams &p, int grid, cudaStream_t stream);           // models without a lane-block class
+// every (sequence, model) pair of the models that have no SSV tiles, appended to the candidate list of the exact kernels
+int launch_ssv_bypass(const int32_t *models, int32_t nbypass, int32_t nseq, const int32_t *len, const int32_t *bin,
+                      const uint8_t *model_active, int32_t nmodels_db, int2 *cand, int32_t *cand_count, int32_t cand_cap,
+                      cudaStream_t stream);
 int launch_msv2(const MsvParams &p, int cls, int grid, cudaStream_t stream);       // lane-blocked, class index 0..9
 
 // ---- stages 2-4: bias filter, ViterbiFilter, ForwardParser on the survivors ----

@@ -214,3 +214,36 @@ def test_region_with_more_domains_than_slots(engine, cpr_models, cpr_oracle, ora
     print('repeat protein (regions, clustered, envelopes):', regions, 'passes repeated:', st.n_queue_retries, 'worst score diff', compare(rows, hits))
     assert regions and regions[0][2] > 64 * regions[0][0] // 2
     assert st.n_queue_retries >= 1
+
+
+def test_search_model_beyond_the_ssv_tiles(engine, oracle, tmp_path):
+    """M = 3,300: the chain of SSV tiles of such a model does not fit shared memory, so it gets none and every pair of it goes
+    straight to the exact MSV kernel (ssv_bypass_kernel); the rest of the cascade runs on the chunked kernels.  Searched next to
+    an ordinary model, as the whole database and as a per-call subset; a model beyond the DP rows (M > 4,608) is refused by name."""
+    p = str(tmp_path / 'long.hmm')
+    ms = synth.make_model_db(p, CPR_HMM, [300, 3300], seed=31)
+    ohf = oracle.HmmFile(p)
+    models = engine.load_models(p)
+    b = synth.make_bin('l', ms, seed=32, n_orfs=40, copies=(2, 3), max_len=4000, split_prob=0.0, tandem_prob=0.0)
+    db = engine.seqdb(b.residues, b.offsets)
+    for idx in (None, [1]):
+        hits = engine.search(models, db) if idx is None else engine.search(models, db, model_idx=idx)
+        rp = oracle.search(ohf, b.residues, b.offsets, nthreads=8, models=idx)
+        rows = oracle.hits_table(rp)
+        oracle.free_results(rp)
+        if idx is not None:
+            for r in rows:
+                r['model'] = idx[r['model']]
+        assert any(r['model'] == 1 for r in rows)
+        short = [(r, h) for r, h in zip(rows, hits) if r['model'] == 0]
+        long_ = [(r, h) for r, h in zip(rows, hits) if r['model'] == 1]
+        assert len(rows) == len(hits)
+        compare([r for r, _ in short], np.array([h for _, h in short], dtype=hits.dtype), exact=True)
+        compare([r for r, _ in long_], np.array([h for _, h in long_], dtype=hits.dtype), exact=False)
+    db.close()
+    models.close()
+    q = str(tmp_path / 'giant.hmm')
+    synth.make_model_db(q, CPR_HMM, [4700], seed=33)
+    from checkm_b200._lib import CkmError
+    with pytest.raises(CkmError, match='4608'):
+        engine.load_models(q)
