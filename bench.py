@@ -43,7 +43,7 @@ sys.path.insert(0, ROOT)
 CPR = os.path.join(ROOT, 'tests', 'golden', 'cpr_43_markers.hmm')
 
 N_MODELS = 5000
-BINS_PER_STEP = 16
+BINS_PER_STEP = 32
 CFG = {2: dict(orfs=1900, n_models=43, total_bins=100), 3: dict(orfs=2900, n_models=N_MODELS, total_bins=None),
        4: dict(orfs=None, n_models=N_MODELS, total_bins=512)}
 
@@ -422,11 +422,11 @@ def main():
         costs = [float(len(b.residues)) * sumM_all for b in allbins]
         mine = sharding.partition_bins(costs, world)[rank]
         mybins = [allbins[int(j)] for j in mine]
-        # batches of at most B bins and ~16 M residues, largest bins first (the tail of the step is then made of small batches)
+        # batches of at most B bins and ~32 M residues, largest bins first (the tail of the step is then made of small batches)
         mybins.sort(key=lambda b: -len(b.residues))
         batches, cur, cur_res = [], [], 0
         for b in mybins:
-            if cur and (len(cur) >= B or cur_res + len(b.residues) > 16 * 1024 * 1024):
+            if cur and (len(cur) >= B or cur_res + len(b.residues) > 32 * 1024 * 1024):
                 batches.append(Batch(cur))
                 cur, cur_res = [], 0
             cur.append(b)

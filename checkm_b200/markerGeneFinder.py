@@ -54,7 +54,7 @@ class MarkerGeneFinder(object):
     def __init__(self, threads):
         self.logger = logging.getLogger('timestamp')
         self.totalThreads = threads
-        self.batch_residues = int(os.environ.get('CKM_BATCH_RESIDUES', str(16 * 1024 * 1024)))      # ~16 bins of 3 Mb per search
+        self.batch_residues = int(os.environ.get('CKM_BATCH_RESIDUES', str(32 * 1024 * 1024)))      # ~32 bins of 3 Mb per search
 
     def find(self, binFiles, outDir, tableOut, hmmerOut, markerFile, bKeepAlignment, bNucORFs, bCalledGenes):
         HMMERRunner()                       # engine present? (exits like the reference when the tool is missing)

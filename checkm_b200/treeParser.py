@@ -15,7 +15,9 @@ What differs from the reference is cost, not results:
   * the marker-set literal of a node is parsed once and shared between the bins that pass through it.
 Reference behaviour kept on purpose: `_getMarkerSet` builds the set from the LAST LABELLED node it looked at, so a walk
 that reaches the root without a node meeting the criteria returns the root's set under the lineage name 'root'; bins are
-written in `os.listdir` order; a `PF` accession is matched against the removal list as `pfamNNNNN` without version."""
+written in `os.listdir` order; a `PF` accession is matched against the removal list as `pfamNNNNN` without version.
+Inside a full CheckM install the class derives from CheckM's own `TreeParser`, so `tree_qa`'s reports keep working and call
+into the methods below; `_findDomainNode` therefore uses only the node API both tree classes share."""
 import logging
 import os
 import sys
@@ -25,8 +27,13 @@ from .markerSets import MarkerSet, BinMarkerSets, _parse_set_list
 from .common import checkDirExists, getBinIdsFromOutDir
 from .util import newick
 
+try:                                              # inside a full CheckM install (dendropy present): CheckM's reports
+    from checkm.treeParser import TreeParser as _ReportBase          # (printSummary, reportBinTaxonomy, ...) stay available
+except Exception:                                 # stand-alone: the selection and the look-ups below are all there is
+    _ReportBase = object
 
-class TreeParser(object):
+
+class TreeParser(_ReportBase):
     def __init__(self):
         self.logger = logging.getLogger('timestamp')
         self.lineageSpecificGenesToRemove = None
@@ -112,7 +119,7 @@ class TreeParser(object):
             if flags is not None:
                 found = flags[id(curNode)]
             else:
-                found = any(leaf.taxon.label.startswith('IMG_') for leaf in curNode.leaf_iter())
+                found = any(leaf.taxon.label.startswith('IMG_') for leaf in curNode.leaf_nodes())
             if found:
                 break
             curNode = curNode.parent_node
@@ -123,7 +130,7 @@ class TreeParser(object):
             head += 1
             if curNode.label:
                 return curNode
-            for child in curNode._children:
+            for child in curNode.child_nodes():
                 if child.is_internal():
                     queue.append(child)
         self.logger.error('Failed to associate bin with a domain. Please report this bug.')
