@@ -34,14 +34,39 @@ constexpr uint32_t VP_TFLOORW = 0xC000C000u;     // -16384 | -16384 : floor of t
 __device__ __forceinline__ int vp_lo(uint32_t w) { return (int)(int16_t)(w & 0xffffu); }
 __device__ __forceinline__ int vp_hi(uint32_t w) { return (int)w >> 16; }
 
+// Work distribution.  Every class kernel reads the one survivor list of the bias filter.  A warp takes 32 consecutive
+// candidates at a time (from the class's cursor p.vit_work[cls]: dynamic, so the long ORFs at the end of the list do not
+// leave a tail; without a cursor, in static strides), each lane looks up the class of one of them -- one coalesced pass
+// over the list per kernel instead of a dependent two-load round trip per candidate and warp -- and the warp then scores
+// the ones that are its own, one after the other.
 template <int W, bool TSMEM>
-__global__ void __launch_bounds__(128) vitp_kernel(FilterParams p) {
+__global__ void __launch_bounds__(128) vitp_kernel(FilterParams p, int cls) {
   extern __shared__ __align__(16) uint8_t vsm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   uint4 *tws = reinterpret_cast<uint4 *>(vsm) + (size_t)warp * W * 64;
   const uint32_t sel = (lane == 0) ? 0x1054u : 0x3210u;
   const int n = min(*p.in_count, p.in_cap);
-  for (int c = blockIdx.x * wpb + warp; c < n; c += gridDim.x * wpb) {
+  int32_t *cursor = (p.vit_work != nullptr) ? p.vit_work + cls : nullptr;
+  for (int64_t it = 0;; ++it) {
+    int64_t base64;
+    if (cursor != nullptr) {
+      int b = 0;
+      if (lane == 0) b = atomicAdd(cursor, 32);
+      base64 = __shfl_sync(0xffffffffu, b, 0);
+    } else {
+      base64 = ((it * gridDim.x + blockIdx.x) * wpb + warp) * 32;
+    }
+    if (base64 >= n) break;
+    const int base = (int)base64;
+    bool mine = false;
+    if (base + lane < n) {
+      const int vq = p.ms[p.in[base + lane].model].vq;
+      mine = (vq == 2 * W) || (W == 1 && vq == 0);
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, mine);
+  while (todo != 0u) {
+    const int c = base + __ffs(todo) - 1;
+    todo &= todo - 1u;
     Candidate cd = p.in[c];
     const int m = cd.model;
     const ModelScalars ms = p.ms[m];
@@ -193,17 +218,18 @@ __global__ void __launch_bounds__(128) vitp_kernel(FilterParams p) {
       if (pos < p.out_cap) p.out[pos] = cd;
       if (p.dense_passed != nullptr) atomicOr_u8(p.dense_passed, (int64_t)p.model_slot[m] * p.nseq + s, 4);
     }
-  }
+  }   // candidates of this group of 32
+  }   // groups
 }
 
 template <int W, bool TSMEM>
-static int launch_vitp_w(const FilterParams &p, int grid, cudaStream_t st) {
+static int launch_vitp_w(const FilterParams &p, int cls, int grid, cudaStream_t st) {
   const int sm = TSMEM ? 4 * W * 64 * (int)sizeof(uint4) : 0;
   if (sm > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(vitp_kernel<W, TSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(vitp)");
   }
-  vitp_kernel<W, TSMEM><<<grid, 128, sm, st>>>(p);
+  vitp_kernel<W, TSMEM><<<grid, 128, sm, st>>>(p, cls);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? CKM_OK : cuda_fail(e, "vitp_kernel launch");
 }
@@ -226,16 +252,16 @@ int launch_all_pairs(Candidate *out, int32_t *count, const int32_t *slot_model, 
 
 int launch_vitp(const FilterParams &p, int cls, int grid, cudaStream_t st) {
   switch (cls) {
-    case 0: return launch_vitp_w<1, false>(p, grid, st);
-    case 1: return launch_vitp_w<2, false>(p, grid, st);
-    case 2: return launch_vitp_w<3, false>(p, grid, st);
-    case 3: return launch_vitp_w<4, false>(p, grid, st);
-    case 4: return launch_vitp_w<6, true>(p, grid, st);
-    case 5: return launch_vitp_w<8, true>(p, grid, st);
-    case 6: return launch_vitp_w<10, true>(p, grid, st);
-    case 7: return launch_vitp_w<12, true>(p, grid, st);
-    case 8: return launch_vitp_w<14, true>(p, grid, st);
-    case 9: return launch_vitp_w<16, true>(p, grid, st);
+    case 0: return launch_vitp_w<1, false>(p, cls, grid, st);
+    case 1: return launch_vitp_w<2, false>(p, cls, grid, st);
+    case 2: return launch_vitp_w<3, false>(p, cls, grid, st);
+    case 3: return launch_vitp_w<4, false>(p, cls, grid, st);
+    case 4: return launch_vitp_w<6, true>(p, cls, grid, st);
+    case 5: return launch_vitp_w<8, true>(p, cls, grid, st);
+    case 6: return launch_vitp_w<10, true>(p, cls, grid, st);
+    case 7: return launch_vitp_w<12, true>(p, cls, grid, st);
+    case 8: return launch_vitp_w<14, true>(p, cls, grid, st);
+    case 9: return launch_vitp_w<16, true>(p, cls, grid, st);
   }
   set_error("launch_vitp: bad class"); return CKM_EINVAL;
 }

@@ -24,7 +24,7 @@ static bool use_blocked_kernels();
 static bool use_packed_viterbi() { const char *v = std::getenv("CKM_VITP"); return use_blocked_kernels() && !(v != nullptr && v[0] == '0'); }
 static int fan_out(ckm_engine *e);
 static int fan_in(ckm_engine *e);
-enum { CTR_UNIT4 = 0, CTR_UNIT8, CTR_UNIT16, CTR_UNIT32, CTR_CAND, CTR_MSV, CTR_BIAS, CTR_VIT, CTR_FWD, CTR_ENV, CTR_DOM, CTR_VREDO, CTR_SSVRES, CTR_N = 32 };
+enum { CTR_UNIT4 = 0, CTR_UNIT8, CTR_UNIT16, CTR_UNIT32, CTR_CAND, CTR_MSV, CTR_BIAS, CTR_VIT, CTR_FWD, CTR_ENV, CTR_DOM, CTR_VREDO, CTR_SSVRES, CTR_VWORK = 16 /* .. 25: cursors of the packed-Viterbi class kernels */, CTR_N = 32 };
 
 struct ActiveMasks {
   DevBuf tile_active, model_active, model_slot;
@@ -222,6 +222,7 @@ static int run_stage2(ckm_engine *e, const ckm_models *m, const ckm_seqdb *db, A
   if (use_packed_viterbi()) {
     // packed int16x2 kernels, one per class; what they cannot score exactly (strong hits near the int16 ceiling, models
     // without a class, pairs outside the safety conditions of kernels_vitp.cu) lands in the redo list ...
+    p.vit_work = e->d_counters + CTR_VWORK;      // zeroed with the other counters at the start of the cascade
     if ((rc = fan_out(e))) return rc;
     for (int c = 0; c < N_BLK_CLASSES; ++c) if ((rc = launch_vitp(p, c, nsm * 8, e->cls[c]))) return rc;
     if ((rc = fan_in(e))) return rc;
@@ -788,6 +789,7 @@ int ckm_viterbi_scores(ckm_engine *e, const ckm_models *m, const int32_t *model_
     p.in = din.as<Candidate>(); p.in_count = e->d_counters + CTR_BIAS; p.in_cap = (int32_t)nf;
     p.out = dout.as<Candidate>(); p.out_count = e->d_counters + CTR_VIT; p.out_cap = (int32_t)nf;
     if (mode == 0) {
+      p.vit_work = e->d_counters + CTR_VWORK;
       if ((rc = fan_out(e))) return rc;
       for (int c = 0; c < N_BLK_CLASSES; ++c) if ((rc = launch_vitp(p, c, nsm * 8, e->cls[c]))) return rc;
       if ((rc = fan_in(e))) return rc;

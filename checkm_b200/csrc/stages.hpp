@@ -74,6 +74,7 @@ struct FilterParams {
   const uint4 *twb; const uint32_t *rwb; const float4 *tfb; const float *rfb;   // lane-blocked tables
   const uint4 *twp; const uint32_t *rwp;                                         // packed Viterbi tables
   Candidate *redo; int32_t *redo_count; int32_t redo_cap;                       // pairs the packed Viterbi kernel hands to the int32 kernels
+  int32_t *vit_work;                 // N_BLK_CLASSES zeroed cursors into `in`, one per packed-Viterbi class kernel (null: static strides)
   const Candidate *in; const int32_t *in_count; int32_t in_cap;
   Candidate *out; int32_t *out_count; int32_t out_cap;
   int32_t row_elems;                 // shared-memory elements of one DP row
