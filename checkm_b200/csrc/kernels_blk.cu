@@ -97,11 +97,13 @@ __global__ void __launch_bounds__(BLK_WARPS * 32) envelope2_kernel(DomdefParams 
     const uint8_t *res = p.res + p.off[pw.seq] + (env.i - 1);
     const Specials sp = make_specials(pw.L, false);
     const int64_t mat = (int64_t)(Ld + 1) * 3 * QW;
-    float *F = p.scratch + env.scratch_off, *Bm = F + mat;
-    float *xf = Bm + mat, *xb = xf + (int64_t)(Ld + 1) * X_NX, *pps = xb + (int64_t)(Ld + 1) * X_NX;
+    // ONE matrix of (Ld + 1) rows x 3 planes per envelope.  Forward fills planes 0 (M) and 2 (I); Backward replaces them in place by
+    // F.B; the optimal-accuracy fill reads row r of F.B and then overwrites that very row with its own M / D / I cells (plane 1
+    // was free until then), so the traceback finds the OA matrix where the Forward matrix used to be.
+    float *F = p.scratch + env.scratch_off, *Bm = F;
+    float *xf = F + mat, *xb = xf + (int64_t)(Ld + 1) * X_NX, *pps = xb + (int64_t)(Ld + 1) * X_NX;
     float *xo = xf;
     float *n2sc = p.n2sc + pw.row_off;
-    // F: Forward matrix (M, I planes) -> replaced in place by F.B during the Backward pass; Bm: later the OA matrix
     const float envsc = forward_blk<Q, TSMEM, true, false>(bm, res, Ld, sp, xf, F);
     __syncwarp();
     backward_blk<Q, TSMEM, 2>(bm, res, Ld, sp, xf, xb, F);

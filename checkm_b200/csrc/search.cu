@@ -345,7 +345,7 @@ static std::vector<float> &logsum_table() {
 }
 
 
-// Envelope rescoring in waves: 2 matrices + specials of scratch per envelope under a fixed budget, every class on its own
+// Envelope rescoring in waves: one matrix (blocked kernels; two for the chunked ones) + specials of scratch per envelope under a fixed budget, every class on its own
 // stream.  leave_last: the last wave is left running on the class streams (the caller joins them with fan_in).
 struct EnvRunner {
   ckm_engine *e; const ckm_models *m; DomdefParams *p; const std::vector<PairWork> *pairs; DevBuf *dscratch;
@@ -375,7 +375,7 @@ static int run_envelope_waves(EnvRunner &R, std::vector<Envelope> &ev, DevBuf &d
     const int64_t Ld = ev[i].j - ev[i].i + 1, Mpad = ((m->models[pw.model].M + 1) + 31) / 32 * 32 + 32;
     const int64_t vq = p.use_blk ? vq_of(m->models[pw.model].M) : 0;
     const int64_t width = vq ? 32 * vq : Mpad;
-    need[i] = 2 * (Ld + 1) * 3 * width + (Ld + 1) * 15 + 64;
+    need[i] = (vq ? 1 : 2) * (Ld + 1) * 3 * width + (Ld + 1) * 15 + 64;      // blocked kernels: the OA matrix overwrites F.B row by row; chunked kernels keep two
     ecls[i] = (int8_t)cls_of(m->models[pw.model].M, p.use_blk != 0);
   }
   const int64_t budget = std::max<int64_t>(R.budget0, *std::max_element(need.begin(), need.end()));
