@@ -362,6 +362,13 @@ static int64_t env_scratch_budget() {
   const size_t neng = (size_t)std::max(1, g_live_engines.load());
   return (int64_t)std::min<size_t>(total_b * 6 / 10 / neng, (size_t)56 << 30) / (int64_t)sizeof(float);
 }
+// floats of scratch one envelope needs (blocked kernels: one matrix, the OA fill overwrites F.B row by row; chunked kernels: two)
+static int64_t envelope_need(const ckm_models *m, const PairWork &pw, const Envelope &en, bool use_blk) {
+  const int64_t Ld = en.j - en.i + 1, Mpad = ((m->models[pw.model].M + 1) + 31) / 32 * 32 + 32;
+  const int64_t vq = use_blk ? vq_of(m->models[pw.model].M) : 0;
+  const int64_t width = vq ? 32 * vq : Mpad;
+  return (vq ? 1 : 2) * (Ld + 1) * 3 * width + (Ld + 1) * 15 + 64;
+}
 static int run_envelope_waves(EnvRunner &R, std::vector<Envelope> &ev, DevBuf &d_ev, DevBuf &d_ord, bool leave_last) {
   if (ev.empty()) return CKM_OK;
   ckm_engine *e = R.e; const ckm_models *m = R.m; DomdefParams &p = *R.p; const std::vector<PairWork> &pairs = *R.pairs;
@@ -372,10 +379,7 @@ static int run_envelope_waves(EnvRunner &R, std::vector<Envelope> &ev, DevBuf &d
   std::vector<int8_t> ecls(ev.size());
   for (size_t i = 0; i < ev.size(); ++i) {
     const PairWork &pw = pairs[ev[i].pair];
-    const int64_t Ld = ev[i].j - ev[i].i + 1, Mpad = ((m->models[pw.model].M + 1) + 31) / 32 * 32 + 32;
-    const int64_t vq = p.use_blk ? vq_of(m->models[pw.model].M) : 0;
-    const int64_t width = vq ? 32 * vq : Mpad;
-    need[i] = (vq ? 1 : 2) * (Ld + 1) * 3 * width + (Ld + 1) * 15 + 64;      // blocked kernels: the OA matrix overwrites F.B row by row; chunked kernels keep two
+    need[i] = envelope_need(m, pw, ev[i], p.use_blk != 0);
     ecls[i] = (int8_t)cls_of(m->models[pw.model].M, p.use_blk != 0);
   }
   const int64_t budget = std::max<int64_t>(R.budget0, *std::max_element(need.begin(), need.end()));
@@ -584,12 +588,19 @@ static int do_search(ckm_engine *e, const ckm_models *m, const int32_t *model_id
       p.doms = ddoms.as<DomainOut>();
       EnvRunner R{e, m, &p, &pairs, &dscratch, env_scratch_budget(), 0, nsm};
       auto run_env_batch = [&](std::vector<Envelope> &ev, DevBuf &d_ev, DevBuf &d_ord, bool leave_last) -> int { return run_envelope_waves(R, ev, d_ev, d_ord, leave_last); };
-      // The trace ensemble of the multi-domain regions (one warp per region, latency-bound, its own stream) is queued first and
-      // runs under the envelope waves of the single-domain regions (class streams).  Next to them its dependent loads take 2-3x
-      // longer than alone, but a 32-bin batch has two envelope waves to hide that under: domain stage 501 -> 485 ms per batch.
-      // CKM_ENS_FIRST=0 queues it after the last wave has been launched instead (better when there is a single short wave).
+      // The trace ensemble of the multi-domain regions (one warp per region, latency-bound, its own stream) runs next to the
+      // envelope kernels of the single-domain regions (class streams).  Next to them its dependent loads take 2-3x longer than
+      // alone.  When the envelopes need more than one wave of scratch (large batches) it is queued FIRST and has all the waves to
+      // hide under (32-bin batch: domain stage 501 -> 485 ms); with a single wave it is queued after the envelope kernels and takes
+      // the SMs as they drain.  CKM_ENS_FIRST=1 / 0 forces one order.
       EnsembleJob *job = nullptr;
-      static const bool ens_first = [] { const char *v = std::getenv("CKM_ENS_FIRST"); return !(v != nullptr && v[0] == '0'); }();
+      static const int ens_knob = [] { const char *v = std::getenv("CKM_ENS_FIRST"); return v == nullptr ? -1 : (v[0] == '0' ? 0 : 1); }();
+      bool ens_first = (ens_knob == 1);
+      if (ens_knob < 0 && !multi_idx.empty()) {
+        int64_t tot = 0;
+        for (const Envelope &en : envs1) tot += envelope_need(m, pairs[en.pair], en, p.use_blk != 0);
+        ens_first = tot > R.budget0;
+      }
       if (ens_first && !multi_idx.empty()) {
         CKM_CUDA(cudaEventRecord(e->fan_ev, st));
         CKM_CUDA(cudaStreamWaitEvent(e->aux, e->fan_ev, 0));
