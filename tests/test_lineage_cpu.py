@@ -143,3 +143,63 @@ def test_newick_reader():
     for bad in ('((a,b);', '(a,b));', "('a,b);", '(a,b):x;', '', '(a[b,c);'):
         with pytest.raises(newick.NewickError):
             newick.Tree.get_from_string(bad)
+
+
+def test_newick_reader_on_random_trees():
+    """Seeded random trees written out with every label style (bare, quoted with blanks / quotes / brackets), optional edge
+    lengths and comments: the reader must give back the generating structure."""
+    import random
+    from checkm_b200.util import newick
+
+    def label(rng, leaf):
+        kind = rng.random()
+        if kind < 0.5:
+            return ('IMG_%d' % rng.randrange(10 ** 6)) if leaf else ('UID%d|k__X;p__Y_%d|%d' % (rng.randrange(999), rng.randrange(99), rng.randrange(101)))
+        if kind < 0.8:
+            return "bin %d (draft)'s [v2]" % rng.randrange(1000)
+        return 'a_b-c.%d' % rng.randrange(1000)
+
+    def quote(s):
+        bare = all(c not in s for c in " ()[]':;,")
+        return s if bare else "'" + s.replace("'", "''") + "'"
+
+    def build(rng, depth):
+        if depth == 0 or rng.random() < 0.3:
+            return (label(rng, True), [])
+        kids = [build(rng, depth - 1) for _ in range(rng.randrange(2, 5))]
+        return (label(rng, False) if rng.random() < 0.6 else None, kids)
+
+    def write(node, rng):
+        lab, kids = node
+        s = ''
+        if kids:
+            s += '(' + ','.join(write(k, rng) for k in kids) + ')'
+        if lab is not None:
+            s += quote(lab)
+        if rng.random() < 0.7:
+            s += ':%g' % rng.uniform(0, 2)
+        if rng.random() < 0.1:
+            s += '[&support=%d]' % rng.randrange(100)
+        return s
+
+    def check(node, got):
+        lab, kids = node
+        if kids:
+            assert got.is_internal() and got.label == lab and got.taxon is None
+            got_kids = got.child_nodes()
+            assert len(got_kids) == len(kids)
+            for k, g in zip(kids, got_kids):
+                assert g.parent_node is got
+                check(k, g)
+        else:
+            assert got.is_leaf() and got.taxon.label == lab and got.label is None
+
+    for seed in range(40):
+        rng = random.Random(seed)
+        tree = (None, [build(rng, 6) for _ in range(2)])
+        text = write(tree, rng) + ';\n'
+        got = newick.Tree.get_from_string(text)
+        check(tree, got.seed_node)
+        leaves = [l.taxon.label for l in got.leaf_nodes()]
+        for name in set(leaves):
+            assert got.find_node_with_taxon_label(name).taxon.label == name
