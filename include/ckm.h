@@ -116,7 +116,10 @@ const char *ckm_version(void);
 int  ckm_device_name(ckm_engine *e, char *buf, int buflen);
 
 /* ---- models: parse HMMER3/f (header AND body), configure MSV/Viterbi/Forward profiles, upload ----
- * replaces hmmsearch's own reading of <hmmfile> and HmmModelParser.simpleParse (hmmerModelParser.py:46-83) */
+ * replaces hmmsearch's own reading of <hmmfile> and HmmModelParser.simpleParse (hmmerModelParser.py:46-83).
+ * A model may have up to 4,608 match positions (the DP rows of the chunked kernels live in shared memory); a longer one makes
+ * the call fail with CKM_EINVAL and the model's name in ckm_last_error().  Models of 3,072 positions and more are searched
+ * without the SSV pre-filter (same results, every pair scored by the exact MSV kernel). */
 int  ckm_models_load(ckm_engine *e, const char *hmm_path, ckm_models **out);
 int  ckm_models_count(const ckm_models *m);
 int  ckm_models_info(const ckm_models *m, int idx, ckm_model_info *out);
